@@ -1,0 +1,211 @@
+/* rrtb.h -- C ABI of librrtb200.so: the B200-native path-tracing core behind rrt's renderer seam.
+ *
+ * This is the drop-in boundary for ONE path of rogerallen/rrt: the renderer that sits behind
+ * `class Rrt` (reference rrt.h:14-48; implementations rrt.cu / rrt.cpp chosen at link time,
+ * reference Makefile:21-22).  Every entry point below names the reference interface it replaces
+ * (file:line under /root/reference).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative rrtb_status on failure; the library never
+ *     calls exit() (the reference does: rrt.cu:31-40) -- the `Rrt` shim in rrt_b200/host maps a
+ *     failure back to the reference's message + exit(99).
+ *   - one context = one GPU.  Multi-GPU = one context (normally one process) per GPU, each
+ *     rendering the shard (rank, world) of the same image; the shards are disjoint-or-additive in a
+ *     64-bit fixed-point accumulator, so any reduction order gives bit-identical images.
+ *   - there is NO CPU fallback: without a CUDA device rrtb_create fails with RRTB_ERR_NO_DEVICE.
+ *   - framebuffer layout is the reference's: index j*W+i, j = 0 is the BOTTOM scanline, value =
+ *     SUM (not mean) over samples of per-sample radiance (rrt.cu:109-121).
+ */
+#ifndef RRTB_H
+#define RRTB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRTB_ABI_VERSION 1
+
+typedef enum rrtb_status {
+    RRTB_OK = 0,
+    RRTB_ERR_INVALID = -1,   /* bad argument */
+    RRTB_ERR_NO_DEVICE = -2, /* no CUDA device / device index out of range */
+    RRTB_ERR_CUDA = -3,      /* a CUDA call failed; see rrtb_last_error */
+    RRTB_ERR_NO_SCENE = -4,  /* render/trace before rrtb_scene_set */
+    RRTB_ERR_IO = -5,        /* file could not be opened (reference exit code 2, scene.h:220-223) */
+    RRTB_ERR_PARSE = -6,     /* malformed scene (reference exit codes 1/3/4) */
+    RRTB_ERR_NOMEM = -7
+} rrtb_status;
+
+/* ---- scene vocabulary (reference scene.h:43-54,183-208; camera.h:40-48) ------------------------
+ * All float, exactly the values the reference's float build (`rrt`) would hold. */
+
+enum { RRTB_LAMBERTIAN = 0, RRTB_METAL = 1, RRTB_DIELECTRIC = 2 }; /* scene.h:183 */
+
+typedef struct rrtb_camera { /* the derived fields of camera.h:8-29 */
+    float origin[3];
+    float lower_left_corner[3];
+    float horizontal[3];
+    float vertical[3];
+    float u[3], v[3], w[3];
+    float lens_radius;
+    float time0, time1; /* shutter open/close */
+} rrtb_camera;
+
+typedef struct rrtb_material {
+    int32_t type;    /* RRTB_LAMBERTIAN | RRTB_METAL | RRTB_DIELECTRIC */
+    float albedo[3]; /* lambertian, metal */
+    float param;     /* metal: fuzz (clamped to <= 1 at use, material.h:48); dielectric: index of refraction */
+} rrtb_material;
+
+typedef struct rrtb_sphere { /* sphere.h:28-31 */
+    float center[3];
+    float radius;
+    int32_t material;
+} rrtb_sphere;
+
+typedef struct rrtb_msphere { /* moving_sphere.h:21-25 */
+    float center0[3], center1[3];
+    float time0, time1;
+    float radius;
+    int32_t material;
+} rrtb_msphere;
+
+typedef struct rrtb_triangle { /* world-space, already instanced (scene.h:157-170); CCW, triangle.h:5-8 */
+    float v0[3], v1[3], v2[3];
+    int32_t material;
+} rrtb_triangle;
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+typedef struct rrtb_ctx rrtb_ctx;
+
+int rrtb_abi_version(void);
+
+/* Replaces `-D <n>` + cudaSetDevice (main.cpp:107-110) and the implicit context of Rrt::render. */
+int rrtb_create(rrtb_ctx **out, int device);
+/* Replaces ~Rrt (rrt.cu:336-342) without the cudaDeviceReset. */
+void rrtb_destroy(rrtb_ctx *ctx);
+/* Last error text for this context (never NULL). ctx may be NULL: returns the last create error. */
+const char *rrtb_last_error(const rrtb_ctx *ctx);
+/* Device facts used by `-q` (main.cpp:13-30) and by bench.py. out[0]=SM count, out[1]=max SM clock kHz,
+ * out[2]=L2 bytes, out[3]=cc major*10+minor. */
+int rrtb_device_info(rrtb_ctx *ctx, int64_t *out4, char *name, int name_len);
+
+/* ---- scene upload + acceleration structure ---------------------------------------------------
+ * Replaces the staging copies (rrt.cu:217-247), create_world<<<1,1>>> (rrt.cu:124-174,266) and the
+ * single-thread recursive bvh_node build (bvh.h:81-159).  Object ids follow the reference's
+ * insertion order: spheres, moving spheres, triangles (rrt.cu:151-164).  With use_bvh != 0 a
+ * GPU LBVH (30-bit Morton codes, radix sort, Karras hierarchy, bottom-up refit) is built on the
+ * device; with use_bvh == 0 (`-b`) rays scan the flat primitive list (hittable_list.h:95-117).
+ * Moving-sphere boxes span [camera.time0, camera.time1] (rrt.cu:169, moving_sphere.h:60-66). */
+int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *materials, int n_materials,
+                   const rrtb_sphere *spheres, int n_spheres, const rrtb_msphere *mspheres, int n_mspheres,
+                   const rrtb_triangle *triangles, int n_triangles, int use_bvh);
+/* Replace only the camera (animation frames that differ in the camera only). */
+int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam);
+
+/* ---- render ------------------------------------------------------------------------------------
+ * Replaces render_init + cuda_render (rrt.cu:81-122, launched rrt.cu:289-298) and ray_color
+ * (rrt.cu:42-79). */
+
+enum { RRTB_SHARD_TILES = 0, RRTB_SHARD_SAMPLES = 1 };
+
+typedef struct rrtb_render_params {
+    int32_t width, height;     /* -w -h   (main.cpp:56-57) */
+    int32_t spp;               /* -s      (main.cpp:58)    */
+    int32_t max_depth;         /* -d      (main.cpp:66)    */
+    uint64_t seed;             /* Philox key; the reference's seed constant is 1984 (rrt.cu:88) */
+    int32_t rank, world;       /* this context renders shard `rank` of `world` (1 GPU: 0,1) */
+    int32_t shard_mode;        /* RRTB_SHARD_TILES: interleaved 8x4-pixel tiles; RRTB_SHARD_SAMPLES: sample ranges */
+    int32_t count_rays;        /* != 0: also count ray segments (stats.rays); same image either way */
+} rrtb_render_params;
+
+typedef struct rrtb_stats {
+    double seconds_render; /* device time of the render kernel(s), CUDA events */
+    double seconds_build;  /* device time of the last rrtb_scene_set (upload + LBVH) */
+    double seconds_resolve;/* fixed-point -> float conversion + device->host copy (rrtb_render only) */
+    uint64_t rays;         /* ray segments traced (closest-hit queries), if count_rays */
+    uint64_t paths;        /* camera paths = pixels_in_shard * spp */
+    int32_t kernel_launches;
+    int32_t reserved;
+} rrtb_stats;
+
+/* Host-buffer entry point (what Rrt::render returns, rrt.h:34): renders this context's shard and
+ * writes 3*W*H floats (RGB sums) to the HOST buffer out_rgb. Pixels outside the shard are 0. */
+int rrtb_render(rrtb_ctx *ctx, const rrtb_render_params *p, float *out_rgb, rrtb_stats *stats);
+
+/* Device-resident entry points (used by the multi-GPU host and bench.py):
+ *   d_accum : DEVICE pointer (this GPU's memory, or a peer GPU's mapped over NVLink) to 3*W*H
+ *             uint64 fixed-point accumulators (value * 2^40), pre-zeroed by the caller.  The kernel
+ *             only ever ADDS (64-bit integer atomics), so several GPUs may target one buffer.
+ * rrtb_render_device enqueues on the context stream and synchronises before returning. */
+int rrtb_render_device(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum, rrtb_stats *stats);
+/* d_out_rgb[k] = float(d_accum[k] * 2^-40), k < n   (device pointers) */
+int rrtb_resolve_device(rrtb_ctx *ctx, const uint64_t *d_accum, float *d_out_rgb, size_t n);
+/* sum 64-bit accumulators: d_dst[k] += d_src[k] (device pointers; d_src may be a peer mapping) */
+int rrtb_accumulate_device(rrtb_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t n);
+
+/* ---- test hooks (parity tests call the same device code the render kernel inlines) ----------- */
+
+/* Closest hit for explicit rays. rays7 = (origin xyz, direction xyz, time) per ray, HOST pointers.
+ * mode 0: flat scan (hittable_list.h:95-117 semantics), mode 1: LBVH traversal.
+ * id[i] = object id or -1; t[i] = ray parameter; rec7 (optional, may be NULL) = p(3), normal(3), front. */
+int rrtb_trace_closest(rrtb_ctx *ctx, const float *rays7, int n, float t_min, int mode, int32_t *id, float *t,
+                       float *rec7);
+/* Primary rays exactly as the render kernel generates them (camera.h:31-38, rrt.cu:112-114) for
+ * pixel indices pix[k] (= j*W+i) and sample index s. */
+int rrtb_camera_rays(rrtb_ctx *ctx, const rrtb_render_params *p, const int32_t *pix, int n, int sample,
+                     float *rays7);
+/* LBVH introspection (all HOST pointers, any may be NULL):
+ *   morton[n]            30-bit code of primitive i (object-id order)
+ *   perm[n]              sorted position k -> object id
+ *   left/right[n-1]      children of internal node i: >=0 internal node, <0 leaf ~k (sorted position)
+ *   parent[2n-1]         parent of internal node i (i<n-1) / of leaf k (n-1+k); root's parent = -1
+ *   node_box[6*(n-1)]    min xyz, max xyz of internal node i
+ *   prim_box[6*n]        min xyz, max xyz of primitive i (object-id order)                       */
+int rrtb_bvh_size(rrtb_ctx *ctx, int32_t *n_prims);
+int rrtb_bvh_download(rrtb_ctx *ctx, uint32_t *morton, uint32_t *perm, int32_t *left, int32_t *right,
+                      int32_t *parent, float *node_box, float *prim_box);
+/* Philox4x32-10 known-answer hook: out[4*i..] = philox(ctr[4*i..], key) computed on the device. */
+int rrtb_philox(rrtb_ctx *ctx, const uint32_t *ctr4, int n, uint32_t key0, uint32_t key1, uint32_t *out4);
+/* material::scatter (material.h:21-32,50-57,76-96) on the device for explicit inputs.
+ * in16 per item : ray o(3) d(3) time, p(3), n(3) (face-forwarded), front, material index, unused
+ * rnd4 per item : the Philox block (4 x uint32) the kernel would have drawn for this bounce
+ * out8 per item : scattered direction(3), attenuation(3), scattered(0/1), unused                  */
+int rrtb_scatter(rrtb_ctx *ctx, const float *in16, const uint32_t *rnd4, int n, float *out8);
+
+/* ---- host side of the drop-in (C++ inside the same library; no GPU needed) -------------------
+ * Scene-file parser with the reference grammar and quirks (scene.h:212-452). */
+
+typedef struct rrtb_scene rrtb_scene;
+
+/* On failure *out = NULL and *ref_exit_code (optional) receives the exit code the reference would
+ * have used (1, 2, 3 or 4); err/err_len (optional) receive the reference's message. */
+int rrtb_scene_parse_file(const char *path, int image_width, int image_height, rrtb_scene **out,
+                          int *ref_exit_code, char *err, int err_len);
+void rrtb_scene_free(rrtb_scene *s);
+/* counts[6] = materials, spheres, moving spheres, triangles (flattened), objs, obj instances */
+int rrtb_scene_counts(const rrtb_scene *s, int32_t *counts6);
+const rrtb_camera *rrtb_scene_camera(const rrtb_scene *s);
+const rrtb_material *rrtb_scene_materials(const rrtb_scene *s);
+const rrtb_sphere *rrtb_scene_spheres(const rrtb_scene *s);
+const rrtb_msphere *rrtb_scene_mspheres(const rrtb_scene *s);
+const rrtb_triangle *rrtb_scene_triangles(const rrtb_scene *s);
+/* rrtb_scene_set with a parsed scene. */
+int rrtb_scene_upload(rrtb_ctx *ctx, const rrtb_scene *s, int use_bvh);
+/* camera.h:8-29 in the reference's float arithmetic. */
+int rrtb_camera_derive(const float lookfrom[3], const float lookat[3], const float vup[3], float vfov,
+                       float aspect_ratio, float aperture, float focus_dist, float time0, float time1,
+                       rrtb_camera *out);
+/* color.h:8-23 + the vertical flip of main.cpp:150-163: rgb_sum (bottom-up sums) -> rgb8 (top-down). */
+int rrtb_tonemap_rgb8(const float *rgb_sum, int width, int height, int spp, uint8_t *rgb8);
+/* PNG writer used where the reference calls stbi_write_png (main.cpp:164). */
+int rrtb_write_png(const char *path, int width, int height, const uint8_t *rgb8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRTB_H */
