@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the rrt hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): scenes/final.txt (488 spheres), 1200x800, 500 spp, depth 50.
+A step = one full render of that image: 480 M camera paths, ~1.21 G ray segments.
+metric = Mrays/s = ray segments (closest-hit queries issued by the bounce loop) / seconds / 1e6.
+
+  value     device-resident: scene + LBVH already in HBM; a step = zero accumulator + render kernel
+            (+ NCCL reduce of the 64-bit accumulators to rank 0 when N > 1) + fixed-point resolve.
+  e2e       through the reference-facing C ABI with HOST buffers: rrtb_scene_set (H2D scene + LBVH build)
+            + rrtb_render (render + resolve + D2H framebuffer) inside the timed region, every step.
+  roofline  FP32-issue roofline of the render kernel: achieved = rays/s x W_ray lane-instr
+            per ray (algorithmic count from the counting build's V_box, V_sph, ... on this very workload)
+            against the issue rate MEASURED on this device by rrtb_probe_issue_rate.
+  N > 1     the image is split by interleaved 8x4 tiles (strong scaling: total work fixed), one process
+            per GPU, accumulators summed with one NCCL reduce (integers: order-independent, bit-identical).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, SPP, DEPTH, SEED = 1200, 800, 500, 50, 1984
+METRIC = "Mrays/s on scenes/final.txt 1200x800 (500 spp, depth 50)"
+UNIT = "Mrays/s"
+
+
+def final_scene():
+    """scenes/final.txt.  Parsed by the product's own parser when the text is staged (oracle/_ref/scenes,
+    which travels to the GPU box); otherwise the committed golden arrays, which are bit-identical to the
+    parse (tests/test_host.py)."""
+    import numpy as np
+
+    from rrt_b200 import Scene, SceneArrays
+
+    for p in (os.path.join(ROOT, "oracle", "_ref", "scenes", "final.txt"), "/root/reference/scenes/final.txt"):
+        if os.path.exists(p):
+            return Scene.from_file(p, W, H).arrays, p
+    d = np.load(os.path.join(ROOT, "tests", "golden", "scene_final.npz"))
+    return SceneArrays.from_npz_dict(d), "tests/golden/scene_final.npz"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def w_ray(st):
+    """Algorithmic FP32 lane-instructions per ray segment (SURVEY 8d convention): ray setup 9, slab test 19,
+    sphere 20, moving sphere 25, triangle 37, hit record 15 + scatter 80 on a hit, sky 15 on a miss."""
+    r = float(st["rays"])
+    vb, vs, vm, vt, h = (st[k] / r for k in ("box_tests", "sphere_tests", "msphere_tests", "triangle_tests", "hits"))
+    return 9 + 19 * vb + 20 * vs + 25 * vm + 37 * vt + h * 95 + (1 - h) * 15, dict(V_box=vb, V_sph=vs, V_msph=vm, V_tri=vt, h=h)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref/rrto = rrt.cpp
+    built with -fopenmp, reference Makefile:45-46) on all host threads, on a bounded sample of the
+    workload: the same scene and image at `REF_SPP` samples per pixel per step (cost is linear in spp).
+    Falls back to the oracle port when the reference binary is absent."""
+    if rank != 0:
+        return
+    import multiprocessing
+
+    ref_spp = 2
+    exe = os.path.join(ROOT, "oracle", "_ref", "rrto")
+    scene_txt = os.path.join(ROOT, "oracle", "_ref", "scenes", "final.txt")
+    cores = multiprocessing.cpu_count()
+    # rays per camera path: a property of the estimator, measured by our counting build on this scene
+    # (2.4913 at 1200x800; the reference's own instrumented value is 2.525)
+    rays_per_path = 2.4913
+    try:
+        with open(os.path.join(ROOT, "profiles", "workload_final.json")) as f:
+            rays_per_path = json.load(f)["rays_per_path"]
+    except Exception:
+        pass
+    times = []
+    kind = "reference"
+    if os.path.exists(exe) and os.path.exists(scene_txt):
+        for i in range(args.warmup + args.steps):
+            r = subprocess.run([exe, "-i", scene_txt, "-w", str(W), "-h", str(H), "-s", str(ref_spp), "-d", str(DEPTH), "-o", "/tmp/_rrto.png"],
+                               capture_output=True, text=True)
+            sec = None
+            for ln in r.stderr.splitlines():
+                if ln.startswith("stats,"):
+                    sec = float(ln.split(",")[-1])
+            if sec is None:
+                raise RuntimeError("rrto produced no stats line: " + r.stderr[-300:])
+            if i >= args.warmup:
+                times.append(sec)
+        sample = "oracle/_ref/rrto (reference rrt.cpp, OpenMP double) final.txt %dx%d at %d spp per step" % (W, H, ref_spp)
+    else:
+        kind = "port"
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_lib import Oracle
+
+        scene, _ = final_scene()
+        orc = Oracle(scene)
+        for i in range(args.warmup + args.steps):
+            t0 = time.time()
+            _, _, cnt = orc.render(W, H, ref_spp, DEPTH, SEED)
+            if i >= args.warmup:
+                times.append(time.time() - t0)
+        rays_per_path = cnt["rays"] / cnt["paths"]
+        sample = "oracle port (rrt_oracle.c, OpenMP) final.txt %dx%d at %d spp per step" % (W, H, ref_spp)
+    sec = sum(times) / len(times)
+    value = W * H * ref_spp * rays_per_path / sec / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "reference scene file scenes/final.txt",
+        "config": {"workload": "scenes/final.txt 1200x800 depth 50, bounded sample: %d spp per step" % ref_spp, "rays_per_path": rays_per_path},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def reference_gpu_baseline(spp=20):
+    """The reference's own rrt.cu rebuilt for sm_100a (oracle/_ref/rrt), timed in the same run on the same
+    scene at a bounded spp (its cost is linear in spp).  Not an optimisation target."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "rrt")
+    scene_txt = os.path.join(ROOT, "oracle", "_ref", "scenes", "final.txt")
+    if not (os.path.exists(exe) and os.path.exists(scene_txt)):
+        return None
+    best = None
+    for tx, ty in ((8, 8), (16, 16), (128, 2)):
+        try:
+            r = subprocess.run([exe, "-i", scene_txt, "-w", str(W), "-h", str(H), "-s", str(spp), "-d", str(DEPTH), "-tx", str(tx), "-ty", str(ty), "-o", "/tmp/_rrt_ref.png"],
+                               capture_output=True, text=True, timeout=600)
+        except Exception:
+            continue
+        for ln in r.stderr.splitlines():
+            if ln.startswith("stats,"):
+                sec = float(ln.split(",")[-1])
+                if best is None or sec < best[0]:
+                    best = (sec, tx, ty)
+    if best is None:
+        return None
+    return {"seconds": best[0], "spp": spp, "block": "%dx%d" % (best[1], best[2])}
+
+
+def cpu_baseline_sample(rays_per_path):
+    """rank 0, N=1 only: the reference CPU path (rrto) on a bounded sample, on the box's host cores."""
+    import multiprocessing
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "rrto")
+    scene_txt = os.path.join(ROOT, "oracle", "_ref", "scenes", "final.txt")
+    cores = multiprocessing.cpu_count()
+    spp = 4
+    if os.path.exists(exe) and os.path.exists(scene_txt):
+        r = subprocess.run([exe, "-i", scene_txt, "-w", str(W), "-h", str(H), "-s", str(spp), "-d", str(DEPTH), "-o", "/tmp/_rrto.png"],
+                           capture_output=True, text=True)
+        for ln in r.stderr.splitlines():
+            if ln.startswith("stats,"):
+                f = ln.split(",")
+                sec, threads = float(f[-1]), int(f[-4])
+                return {"value": W * H * spp * rays_per_path / sec / 1e6, "unit": UNIT, "cores": threads, "kind": "reference",
+                        "sample": "oracle/_ref/rrto (reference rrt.cpp, OpenMP, double) final.txt %dx%d, %d spp, %.2f s" % (W, H, spp, sec)}
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+
+    scene, _ = final_scene()
+    t0 = time.time()
+    _, _, cnt = Oracle(scene).render(W, H, spp, DEPTH, SEED)
+    sec = time.time() - t0
+    return {"value": cnt["rays"] / sec / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle port (OpenMP) final.txt %dx%d, %d spp, %.2f s" % (W, H, spp, sec)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spp", type=int, default=SPP, help="debug only: any value other than 500 is not the headline config")
+    ap.add_argument("--no-baselines", action="store_true", help="skip the cpu / reference-GPU baselines (profiling runs)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from rrt_b200 import Context
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    spp = args.spp
+
+    scene, scene_src = final_scene()
+    ctx = Context(local_rank)
+    ctx.set_scene(scene, use_bvh=True)
+    n = 3 * W * H
+    acc = torch.zeros(n, dtype=torch.int64, device=dev)
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    params = ctx.params(W, H, spp, DEPTH, SEED, rank, world, 0, False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kernel_seconds = []
+
+    def step():
+        flush.fill_(1.0)  # L2 flush between timed iterations (the scene itself is far smaller than L2)
+        acc.zero_()
+        torch.cuda.synchronize()  # ctx renders on its own stream
+        st = ctx.render_device(params, acc.data_ptr())
+        kernel_seconds.append(st["seconds_render"])
+        if world > 1:
+            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+        if rank == 0:
+            ctx.resolve_device(acc.data_ptr(), out.data_ptr(), n)
+
+    # counting pass (untimed): rays and per-ray work of exactly this workload and shard
+    pc = ctx.params(W, H, spp, DEPTH, SEED, rank, world, 0, True)
+    acc.zero_()
+    torch.cuda.synchronize()
+    cst = ctx.render_device(pc, acc.data_ptr())
+    counts = torch.tensor([cst[k] for k in ("rays", "box_tests", "sphere_tests", "msphere_tests", "triangle_tests", "hits", "paths")],
+                          dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts)
+    tot = dict(zip(("rays", "box_tests", "sphere_tests", "msphere_tests", "triangle_tests", "hits", "paths"), counts.tolist()))
+    total_rays = tot["rays"]
+
+    for _ in range(args.warmup):
+        step()
+    kernel_seconds.clear()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+    # max over ranks of the device-timed region
+    tt = torch.tensor([dev_s, wall, sum(kernel_seconds) / len(kernel_seconds)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_s, wall, kern_s = tt.tolist()
+    sec_per_step = dev_s / args.steps
+    value = total_rays / sec_per_step / 1e6
+
+    # ---- e2e: through the C ABI with host buffers, every step: scene upload + LBVH build + render + D2H
+    host_out = np.empty((H, W, 3), np.float32)
+    h2d = scene.camera.nbytes + scene.materials.nbytes + scene.spheres.nbytes + scene.mspheres.nbytes + scene.triangles.nbytes
+    d2h = host_out.nbytes if rank == 0 else 0
+
+    def e2e_step():
+        ctx.set_scene(scene, use_bvh=True)
+        if world == 1:
+            ctx.render(W, H, spp, DEPTH, SEED, out=host_out)
+        else:
+            acc.zero_()
+            torch.cuda.synchronize()
+            ctx.render_device(params, acc.data_ptr())
+            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+            if rank == 0:
+                ctx.resolve_device(acc.data_ptr(), out.data_ptr(), n)
+                host_out.reshape(-1)[:] = out.cpu().numpy()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = total_rays / (e2e_t.item() / e2e_steps) / 1e6
+
+    if rank == 0:
+        wr, v = w_ray(tot)
+        probe = ctx.probe_issue_rate()
+        kern_rays_per_s = (cst["rays"] if world == 1 else tot["rays"] / world) / kern_s
+        achieved = kern_rays_per_s * wr  # lane-instr / s, per GPU
+        peak = probe["ffma_fmnmx_mix"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (f64 leaf discriminants, u64 fixed-point accumulation)", "data": "synthetic-free: reference scene file scenes/final.txt (%s)" % scene_src,
+            "config": {"workload": "scenes/final.txt 1200x800, %d spp, depth 50 (BASELINE.json configs[1])" % spp, "prims": scene.n_objects,
+                       "sharding": "one image, interleaved 8x4 tiles over %d GPU(s), NCCL reduce of u64 accumulators" % world,
+                       "l2": "256 MiB flush written between timed iterations", "rays_per_step": total_rays,
+                       "rays_per_path": total_rays / tot["paths"], **{k: round(x, 4) for k, x in v.items()}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "what": "rrtb_scene_set (upload + LBVH build) + rrtb_render (render + resolve + D2H) per step"},
+            "gpu_launches": args.steps * 2,
+            "kernel": {"name": "rrtb::k_render<true,false>", "avg_ms": kern_s * 1e3, "share_of_step": kern_s / sec_per_step},
+            "roofline": {"bound": "fp32_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T lane-instr/s",
+                         "frac": achieved / peak, "traffic": None, "w_ray": wr,
+                         "peak_source": "measured on this device: rrtb_probe_issue_rate FFMA+FMNMX mix (FFMA only: %.2f T/s); "
+                                        "MEASURED_PEAKS.json has no FP32 figure" % (probe["ffma"] / 1e12),
+                         "hbm_note": "scene + LBVH = %d KB, L1/L2 resident: HBM traffic is the 23 MB accumulator only" % ((scene.n_objects * (64 + 48 + 8)) // 1024)},
+            "clocks": clocks,
+            "wall_s": wall,
+        }
+        if world == 1 and not args.no_baselines:
+            line["cpu_baseline"] = cpu_baseline_sample(total_rays / tot["paths"])
+            g = reference_gpu_baseline()
+            if g:
+                g["Mrays/s"] = W * H * g["spp"] * (total_rays / tot["paths"]) / g["seconds"] / 1e6
+                g["what"] = "reference rrt.cu rebuilt for sm_100a (oracle/_ref/rrt), float, its own BVH, best of 3 block shapes"
+                line["reference_gpu"] = g
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

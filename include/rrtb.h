@@ -129,6 +129,11 @@ typedef struct rrtb_stats {
     double seconds_resolve;/* fixed-point -> float conversion + device->host copy (rrtb_render only) */
     uint64_t rays;         /* ray segments traced (closest-hit queries), if count_rays */
     uint64_t paths;        /* camera paths = pixels_in_shard * spp */
+    uint64_t box_tests;    /* counting build only: slab tests, */
+    uint64_t sphere_tests; /*   sphere / moving-sphere / triangle tests and */
+    uint64_t msphere_tests;
+    uint64_t triangle_tests;
+    uint64_t hits;         /*   segments that hit something (V_box, V_sph, V_msph, V_tri, h) */
     int32_t kernel_launches;
     int32_t reserved;
 } rrtb_stats;
@@ -147,6 +152,10 @@ int rrtb_render_device(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_a
 int rrtb_resolve_device(rrtb_ctx *ctx, const uint64_t *d_accum, float *d_out_rgb, size_t n);
 /* sum 64-bit accumulators: d_dst[k] += d_src[k] (device pointers; d_src may be a peer mapping) */
 int rrtb_accumulate_device(rrtb_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t n);
+
+/* Measurement aid (no reference counterpart): the FP32-issue roofline denominator measured on
+ * THIS device -- lane-instructions per second of an FFMA-only loop and of an FFMA+FMNMX (slab-test) mix. */
+int rrtb_probe_issue_rate(rrtb_ctx *ctx, double *ffma_lane_instr_per_s, double *mix_lane_instr_per_s);
 
 /* ---- test hooks (parity tests call the same device code the render kernel inlines) ----------- */
 

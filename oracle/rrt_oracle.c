@@ -217,24 +217,31 @@ static inline f3 msphere_center(const rrtb_msphere *m, float time)
               fmaf(k, m->center1[2] - m->center0[2], m->center0[2]));
 }
 
-/* triangle.h:35-75 (Moeller-Trumbore), products accumulated in double from the float inputs. */
-static int triangle_t(f3 o, f3 d, f3 v0, f3 v1, f3 v2, float t_min, float t_max, float *t_out)
+/* triangle.h:35-75 (Moeller-Trumbore).  Products are accumulated in double from the float inputs with
+ * fixed fma chains; the barycentric tests are done on the numerators (no division):  with det = a,
+ * u = un/det, v = vn/det the reference's  u<0 || u>1 || v<0 || u+v>1  is evaluated sign-aware.
+ * t = float(tn) / float(det). */
+static inline double dcross(double a, double b, double c, double d) { return fma(a, b, -(c * d)); } /* a*b - c*d */
+static int triangle_t(f3 o, f3 d, f3 v0, f3 e1f, f3 e2f, float t_min, float t_max, float *t_out)
 {
     const double EPS = (double)1e-7f;
-    f3 e1f = sub3(v1, v0), e2f = sub3(v2, v0);
     double e1x = e1f.x, e1y = e1f.y, e1z = e1f.z, e2x = e2f.x, e2y = e2f.y, e2z = e2f.z;
     double dx = d.x, dy = d.y, dz = d.z;
-    double hx = dy * e2z - dz * e2y, hy = dz * e2x - dx * e2z, hz = dx * e2y - dy * e2x;
-    double a = e1x * hx + e1y * hy + e1z * hz;
-    if (a > -EPS && a < EPS) return 0;
-    double f = 1.0 / a;
+    double hx = dcross(dy, e2z, dz, e2y), hy = dcross(dz, e2x, dx, e2z), hz = dcross(dx, e2y, dy, e2x);
+    double det = fma(e1z, hz, fma(e1y, hy, e1x * hx));
+    if (det > -EPS && det < EPS) return 0;
     double sx = (double)o.x - (double)v0.x, sy = (double)o.y - (double)v0.y, sz = (double)o.z - (double)v0.z;
-    double u = f * (sx * hx + sy * hy + sz * hz);
-    if (u < 0.0 || u > 1.0) return 0;
-    double qx = sy * e1z - sz * e1y, qy = sz * e1x - sx * e1z, qz = sx * e1y - sy * e1x;
-    double v = f * (dx * qx + dy * qy + dz * qz);
-    if (v < 0.0 || u + v > 1.0) return 0;
-    float t = (float)(f * (e2x * qx + e2y * qy + e2z * qz));
+    double un = fma(sz, hz, fma(sy, hy, sx * hx));
+    double qx = dcross(sy, e1z, sz, e1y), qy = dcross(sz, e1x, sx, e1z), qz = dcross(sx, e1y, sy, e1x);
+    double vn = fma(dz, qz, fma(dy, qy, dx * qx));
+    if (det > 0.0) {
+        if (un < 0.0 || un > det || vn < 0.0 || un + vn > det) return 0;
+    }
+    else {
+        if (un > 0.0 || un < det || vn > 0.0 || un + vn < det) return 0;
+    }
+    double tn = fma(e2z, qz, fma(e2y, qy, e2x * qx));
+    float t = (float)tn / (float)det;
     if (t > 1e-7f && t > t_min && t < t_max) { /* exclusive, triangle.h:61 */
         *t_out = t;
         return 1;
@@ -260,7 +267,7 @@ static int hit_t_only(const orc_scene *s, int id, f3 o, f3 d, float time, float 
         return sphere_roots(o, d, msphere_center(m, time), m->radius, t_min, t_max, t);
     }
     const rrtb_triangle *tr = &s->triangles[r.idx];
-    return triangle_t(o, d, ld3(tr->v0), ld3(tr->v1), ld3(tr->v2), t_min, t_max, t);
+    return triangle_t(o, d, ld3(tr->v0), sub3(ld3(tr->v1), ld3(tr->v0)), sub3(ld3(tr->v2), ld3(tr->v0)), t_min, t_max, t);
 }
 
 /* hit_record fill: sphere.h:51-55, moving_sphere.h:51-55, triangle.h:62-66, hittable.h:16-20 */

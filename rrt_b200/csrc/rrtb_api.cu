@@ -1,0 +1,485 @@
+// rrtb_api.cu -- the C ABI of librrtb200.so (include/rrtb.h): context, scene upload, render, test hooks.
+// The reference interfaces each entry point replaces are cited in include/rrtb.h.
+#include "rrtb_internal.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+namespace rrtb {
+
+static std::string g_create_error;
+static std::mutex g_mutex;
+
+int cuda_fail(rrtb_ctx *ctx, cudaError_t e, const char *expr, const char *file, int line)
+{
+    // same wording as the reference's check_cuda (rrt.cu:31-40), plus the CUDA error string
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error = %u at %s:%d '%s' (%s)", (unsigned)e, file, line, expr,
+             cudaGetErrorString(e));
+    if (ctx) ctx->err = buf;
+    else {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        g_create_error = buf;
+    }
+    cudaGetLastError(); // clear the sticky-less error state
+    return RRTB_ERR_CUDA;
+}
+
+int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_msphere *d_msph, const rrtb_triangle *d_tri);
+
+static int invalid(rrtb_ctx *ctx, const char *msg)
+{
+    if (ctx) ctx->err = msg;
+    return RRTB_ERR_INVALID;
+}
+
+template <typename T>
+static int dev_alloc(rrtb_ctx *ctx, T *&p, size_t count)
+{
+    if (count == 0) count = 1;
+    RRTB_CUDA(ctx, cudaMalloc((void **)&p, count * sizeof(T)));
+    return RRTB_OK;
+}
+
+} // namespace rrtb
+
+using namespace rrtb;
+
+extern "C" {
+
+int rrtb_abi_version(void) { return RRTB_ABI_VERSION; }
+
+int rrtb_create(rrtb_ctx **out, int device)
+{
+    if (!out) return RRTB_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                         "); librrtb200 has no CPU fallback";
+        cudaGetLastError();
+        return RRTB_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        g_create_error = "device index out of range";
+        return RRTB_ERR_NO_DEVICE;
+    }
+    rrtb_ctx *ctx = new rrtb_ctx();
+    ctx->device = device;
+    auto fail = [&](int rc) {
+        {
+            std::lock_guard<std::mutex> lk(g_mutex);
+            g_create_error = ctx->err;
+        }
+        delete ctx;
+        return rc;
+    };
+#define CREATE_CUDA(expr)                                                            \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) return fail(cuda_fail(ctx, _e, #expr, __FILE__, __LINE__)); \
+    } while (0)
+    CREATE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreate(&ctx->ev0));
+    CREATE_CUDA(cudaEventCreate(&ctx->ev1));
+    CREATE_CUDA(cudaMalloc((void **)&ctx->d_counters, 8 * sizeof(unsigned long long)));
+#undef CREATE_CUDA
+    *out = ctx;
+    return RRTB_OK;
+}
+
+void rrtb_destroy(rrtb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    free_scene(ctx);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_accum) cudaFree(ctx->d_accum);
+    if (ctx->d_rgb) cudaFree(ctx->d_rgb);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *rrtb_last_error(const rrtb_ctx *ctx)
+{
+    if (ctx) return ctx->err.c_str();
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lk(g_mutex);
+    copy = g_create_error;
+    return copy.c_str();
+}
+
+int rrtb_device_info(rrtb_ctx *ctx, int64_t *out4, char *name, int name_len)
+{
+    if (!ctx) return RRTB_ERR_INVALID;
+    cudaDeviceProp prop;
+    RRTB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    if (out4) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        out4[0] = prop.multiProcessorCount;
+        out4[1] = khz;
+        out4[2] = prop.l2CacheSize;
+        out4[3] = prop.major * 10 + prop.minor;
+    }
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return RRTB_OK;
+}
+
+int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *materials, int n_materials,
+                   const rrtb_sphere *spheres, int n_spheres, const rrtb_msphere *mspheres, int n_mspheres,
+                   const rrtb_triangle *triangles, int n_triangles, int use_bvh)
+{
+    if (!ctx) return RRTB_ERR_INVALID;
+    if (!cam || !materials || n_materials <= 0) return invalid(ctx, "scene needs a camera and at least one material");
+    if (n_spheres < 0 || n_mspheres < 0 || n_triangles < 0) return invalid(ctx, "negative primitive count");
+    const long long n_ll = (long long)n_spheres + n_mspheres + n_triangles;
+    if (n_ll <= 0) return invalid(ctx, "scene has no objects");
+    if (n_ll >= (1ll << 29)) return invalid(ctx, "too many primitives (limit 2^29)");
+    if ((n_spheres && !spheres) || (n_mspheres && !mspheres) || (n_triangles && !triangles))
+        return invalid(ctx, "null primitive array");
+    const int n = (int)n_ll;
+    for (int i = 0; i < n_spheres; ++i)
+        if (spheres[i].material < 0 || spheres[i].material >= n_materials) return invalid(ctx, "sphere material index out of range");
+    for (int i = 0; i < n_mspheres; ++i)
+        if (mspheres[i].material < 0 || mspheres[i].material >= n_materials) return invalid(ctx, "msphere material index out of range");
+    for (int i = 0; i < n_triangles; ++i)
+        if (triangles[i].material < 0 || triangles[i].material >= n_materials) return invalid(ctx, "triangle material index out of range");
+
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    free_scene(ctx);
+    ctx->cam = *cam;
+    ctx->n_materials = n_materials;
+    ctx->n_spheres = n_spheres;
+    ctx->n_mspheres = n_mspheres;
+    ctx->n_triangles = n_triangles;
+    ctx->n_prims = n;
+    ctx->use_bvh = use_bvh ? 1 : 0;
+
+    int rc;
+    const int nb = (n + 255) / 256;
+    const int n_seg = (n + 1023) / 1024;
+    if ((rc = dev_alloc(ctx, ctx->d_prim, (size_t)3 * n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_prim_info, (size_t)n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_materials, (size_t)n_materials))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_material_type, (size_t)n_materials))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_prim_box, (size_t)6 * n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_morton, (size_t)n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_keys, (size_t)n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_keys_tmp, (size_t)n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_left, (size_t)n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_right, (size_t)n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_parent, (size_t)2 * n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_node_box, (size_t)6 * n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_visit, (size_t)n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_nodes, (size_t)4 * n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_leaves, (size_t)3 * n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_leaf_info, (size_t)n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_reduce, (size_t)nb * 7 + 16))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_hist, (size_t)256 * n_seg))) return rc;
+
+    // materials -> (albedo.xyz, param) + type
+    std::vector<float4> mats((size_t)n_materials);
+    std::vector<int> mtypes((size_t)n_materials);
+    for (int i = 0; i < n_materials; ++i) {
+        const rrtb_material &m = materials[i];
+        if (m.type < 0 || m.type > 2) return invalid(ctx, "unknown material type");
+        mats[i] = make_float4(m.albedo[0], m.albedo[1], m.albedo[2], m.param);
+        mtypes[i] = m.type;
+    }
+
+    // staged raw structs (freed after the build)
+    rrtb_sphere *d_sph = nullptr;
+    rrtb_msphere *d_msph = nullptr;
+    rrtb_triangle *d_tri = nullptr;
+    auto cleanup = [&]() {
+        if (d_sph) cudaFree(d_sph);
+        if (d_msph) cudaFree(d_msph);
+        if (d_tri) cudaFree(d_tri);
+    };
+    cudaStream_t st = ctx->stream;
+#define SET_CUDA(expr)                                                      \
+    do {                                                                    \
+        cudaError_t _e = (expr);                                            \
+        if (_e != cudaSuccess) {                                            \
+            cleanup();                                                      \
+            return cuda_fail(ctx, _e, #expr, __FILE__, __LINE__);           \
+        }                                                                   \
+    } while (0)
+    SET_CUDA(cudaEventRecord(ctx->ev0, st));
+    SET_CUDA(cudaMemcpyAsync(ctx->d_materials, mats.data(), sizeof(float4) * n_materials, cudaMemcpyHostToDevice, st));
+    SET_CUDA(cudaMemcpyAsync(ctx->d_material_type, mtypes.data(), sizeof(int) * n_materials, cudaMemcpyHostToDevice, st));
+    if (n_spheres) {
+        SET_CUDA(cudaMalloc((void **)&d_sph, sizeof(rrtb_sphere) * (size_t)n_spheres));
+        SET_CUDA(cudaMemcpyAsync(d_sph, spheres, sizeof(rrtb_sphere) * (size_t)n_spheres, cudaMemcpyHostToDevice, st));
+    }
+    if (n_mspheres) {
+        SET_CUDA(cudaMalloc((void **)&d_msph, sizeof(rrtb_msphere) * (size_t)n_mspheres));
+        SET_CUDA(cudaMemcpyAsync(d_msph, mspheres, sizeof(rrtb_msphere) * (size_t)n_mspheres, cudaMemcpyHostToDevice, st));
+    }
+    if (n_triangles) {
+        SET_CUDA(cudaMalloc((void **)&d_tri, sizeof(rrtb_triangle) * (size_t)n_triangles));
+        SET_CUDA(cudaMemcpyAsync(d_tri, triangles, sizeof(rrtb_triangle) * (size_t)n_triangles, cudaMemcpyHostToDevice, st));
+    }
+    rc = prepare_and_build(ctx, d_sph, d_msph, d_tri);
+    if (rc) {
+        cleanup();
+        return rc;
+    }
+    SET_CUDA(cudaEventRecord(ctx->ev1, st));
+    SET_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    SET_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+#undef SET_CUDA
+    cleanup();
+    ctx->seconds_build = ms * 1e-3;
+    ctx->has_scene = true;
+    return RRTB_OK;
+}
+
+int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam)
+{
+    if (!ctx || !cam) return RRTB_ERR_INVALID;
+    if (!ctx->has_scene) {
+        ctx->err = "no scene";
+        return RRTB_ERR_NO_SCENE;
+    }
+    if (ctx->n_mspheres > 0 && (cam->time0 != ctx->cam.time0 || cam->time1 != ctx->cam.time1))
+        return invalid(ctx, "shutter interval changed with moving spheres present: call rrtb_scene_set");
+    ctx->cam = *cam;
+    return RRTB_OK;
+}
+
+static int check_render(rrtb_ctx *ctx, const rrtb_render_params *p)
+{
+    if (!ctx || !p) return RRTB_ERR_INVALID;
+    if (!ctx->has_scene) {
+        ctx->err = "render before rrtb_scene_set";
+        return RRTB_ERR_NO_SCENE;
+    }
+    if (p->width < 2 || p->height < 2) return invalid(ctx, "image must be at least 2x2 (u = (i+xi)/(W-1), rrt.cu:112)");
+    if (p->spp < 1 || p->max_depth < 0) return invalid(ctx, "spp must be >= 1 and max_depth >= 0");
+    if ((long long)p->width * p->height >= (1ll << 31)) return invalid(ctx, "image too large");
+    if (p->world > 1 && (p->rank < 0 || p->rank >= p->world)) return invalid(ctx, "rank out of range");
+    if (p->shard_mode != RRTB_SHARD_TILES && p->shard_mode != RRTB_SHARD_SAMPLES) return invalid(ctx, "bad shard_mode");
+    return RRTB_OK;
+}
+
+int rrtb_render_device(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum, rrtb_stats *stats)
+{
+    int rc = check_render(ctx, p);
+    if (rc) return rc;
+    if (!d_accum) return invalid(ctx, "null accumulator");
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_render(ctx, p, d_accum, stats);
+}
+
+int rrtb_resolve_device(rrtb_ctx *ctx, const uint64_t *d_accum, float *d_out_rgb, size_t n)
+{
+    if (!ctx || !d_accum || !d_out_rgb) return RRTB_ERR_INVALID;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = launch_resolve(ctx, d_accum, d_out_rgb, n);
+    if (rc) return rc;
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RRTB_OK;
+}
+
+int rrtb_accumulate_device(rrtb_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t n)
+{
+    if (!ctx || !d_dst || !d_src) return RRTB_ERR_INVALID;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = launch_accumulate(ctx, d_dst, d_src, n);
+    if (rc) return rc;
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RRTB_OK;
+}
+
+int rrtb_render(rrtb_ctx *ctx, const rrtb_render_params *p, float *out_rgb, rrtb_stats *stats)
+{
+    int rc = check_render(ctx, p);
+    if (rc) return rc;
+    if (!out_rgb) return invalid(ctx, "null output buffer");
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)3 * p->width * p->height;
+    if (ctx->accum_elems < n) {
+        if (ctx->d_accum) cudaFree(ctx->d_accum);
+        if (ctx->d_rgb) cudaFree(ctx->d_rgb);
+        ctx->d_accum = nullptr;
+        ctx->d_rgb = nullptr;
+        ctx->accum_elems = 0;
+        RRTB_CUDA(ctx, cudaMalloc((void **)&ctx->d_accum, n * sizeof(unsigned long long)));
+        RRTB_CUDA(ctx, cudaMalloc((void **)&ctx->d_rgb, n * sizeof(float)));
+        ctx->accum_elems = n;
+    }
+    RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_accum, 0, n * sizeof(unsigned long long), ctx->stream));
+    rrtb_stats local;
+    memset(&local, 0, sizeof(local));
+    rc = launch_render(ctx, p, (uint64_t *)ctx->d_accum, &local);
+    if (rc) return rc;
+    cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
+    RRTB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    rc = launch_resolve(ctx, (const uint64_t *)ctx->d_accum, ctx->d_rgb, n);
+    if (rc) return rc;
+    RRTB_CUDA(ctx, cudaMemcpyAsync(out_rgb, ctx->d_rgb, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    RRTB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    local.seconds_resolve = ms * 1e-3;
+    local.kernel_launches += 1;
+    if (stats) *stats = local;
+    return RRTB_OK;
+}
+
+int rrtb_probe_issue_rate(rrtb_ctx *ctx, double *ffma_lane_instr_per_s, double *mix_lane_instr_per_s)
+{
+    if (!ctx) return RRTB_ERR_INVALID;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (ffma_lane_instr_per_s && (rc = launch_probe(ctx, 0, ffma_lane_instr_per_s))) return rc;
+    if (mix_lane_instr_per_s && (rc = launch_probe(ctx, 1, mix_lane_instr_per_s))) return rc;
+    return RRTB_OK;
+}
+
+// ---- test hooks ------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf()
+    {
+        if (p) cudaFree(p);
+    }
+};
+} // namespace
+
+#define HOOK_ALLOC(buf, bytes) RRTB_CUDA(ctx, cudaMalloc(&(buf).p, (bytes) ? (bytes) : 1))
+
+int rrtb_trace_closest(rrtb_ctx *ctx, const float *rays7, int n, float t_min, int mode, int32_t *id, float *t,
+                       float *rec7)
+{
+    if (!ctx || !rays7 || !id || !t || n < 0) return RRTB_ERR_INVALID;
+    if (!ctx->has_scene) {
+        ctx->err = "trace before rrtb_scene_set";
+        return RRTB_ERR_NO_SCENE;
+    }
+    if (n == 0) return RRTB_OK;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dr, di, dt, drec;
+    HOOK_ALLOC(dr, sizeof(float) * 7 * (size_t)n);
+    HOOK_ALLOC(di, sizeof(int) * (size_t)n);
+    HOOK_ALLOC(dt, sizeof(float) * (size_t)n);
+    if (rec7) HOOK_ALLOC(drec, sizeof(float) * 7 * (size_t)n);
+    RRTB_CUDA(ctx, cudaMemcpyAsync(dr.p, rays7, sizeof(float) * 7 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_trace(ctx, (const float *)dr.p, n, t_min, mode ? 1 : 0, (int32_t *)di.p, (float *)dt.p,
+                          rec7 ? (float *)drec.p : nullptr);
+    if (rc) return rc;
+    RRTB_CUDA(ctx, cudaMemcpyAsync(id, di.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaMemcpyAsync(t, dt.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rec7) RRTB_CUDA(ctx, cudaMemcpyAsync(rec7, drec.p, sizeof(float) * 7 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RRTB_OK;
+}
+
+int rrtb_camera_rays(rrtb_ctx *ctx, const rrtb_render_params *p, const int32_t *pix, int n, int sample, float *rays7)
+{
+    if (!ctx || !p || !pix || !rays7 || n < 0) return RRTB_ERR_INVALID;
+    if (!ctx->has_scene) {
+        ctx->err = "camera rays before rrtb_scene_set";
+        return RRTB_ERR_NO_SCENE;
+    }
+    if (n == 0) return RRTB_OK;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dp, dr;
+    HOOK_ALLOC(dp, sizeof(int) * (size_t)n);
+    HOOK_ALLOC(dr, sizeof(float) * 7 * (size_t)n);
+    RRTB_CUDA(ctx, cudaMemcpyAsync(dp.p, pix, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_camera_rays(ctx, p, (const int32_t *)dp.p, n, sample, (float *)dr.p);
+    if (rc) return rc;
+    RRTB_CUDA(ctx, cudaMemcpyAsync(rays7, dr.p, sizeof(float) * 7 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RRTB_OK;
+}
+
+int rrtb_bvh_size(rrtb_ctx *ctx, int32_t *n_prims)
+{
+    if (!ctx || !n_prims) return RRTB_ERR_INVALID;
+    if (!ctx->has_scene) return RRTB_ERR_NO_SCENE;
+    *n_prims = ctx->n_prims;
+    return RRTB_OK;
+}
+
+int rrtb_bvh_download(rrtb_ctx *ctx, uint32_t *morton, uint32_t *perm, int32_t *left, int32_t *right,
+                      int32_t *parent, float *node_box, float *prim_box)
+{
+    if (!ctx) return RRTB_ERR_INVALID;
+    if (!ctx->has_scene) return RRTB_ERR_NO_SCENE;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->n_prims, ni = n > 0 ? n - 1 : 0;
+    if (morton) RRTB_CUDA(ctx, cudaMemcpy(morton, ctx->d_morton, 4 * n, cudaMemcpyDeviceToHost));
+    if (perm) {
+        std::vector<uint64_t> keys(n);
+        RRTB_CUDA(ctx, cudaMemcpy(keys.data(), ctx->d_keys, 8 * n, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < n; ++k) perm[k] = (uint32_t)keys[k];
+    }
+    if (left && ni) RRTB_CUDA(ctx, cudaMemcpy(left, ctx->d_left, 4 * ni, cudaMemcpyDeviceToHost));
+    if (right && ni) RRTB_CUDA(ctx, cudaMemcpy(right, ctx->d_right, 4 * ni, cudaMemcpyDeviceToHost));
+    if (parent) RRTB_CUDA(ctx, cudaMemcpy(parent, ctx->d_parent, 4 * (2 * n - 1), cudaMemcpyDeviceToHost));
+    if (node_box && ni) RRTB_CUDA(ctx, cudaMemcpy(node_box, ctx->d_node_box, 4 * 6 * ni, cudaMemcpyDeviceToHost));
+    if (prim_box) RRTB_CUDA(ctx, cudaMemcpy(prim_box, ctx->d_prim_box, 4 * 6 * n, cudaMemcpyDeviceToHost));
+    return RRTB_OK;
+}
+
+int rrtb_philox(rrtb_ctx *ctx, const uint32_t *ctr4, int n, uint32_t key0, uint32_t key1, uint32_t *out4)
+{
+    if (!ctx || !ctr4 || !out4 || n < 0) return RRTB_ERR_INVALID;
+    if (n == 0) return RRTB_OK;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dc, dout;
+    HOOK_ALLOC(dc, 16 * (size_t)n);
+    HOOK_ALLOC(dout, 16 * (size_t)n);
+    RRTB_CUDA(ctx, cudaMemcpyAsync(dc.p, ctr4, 16 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_philox(ctx, (const uint32_t *)dc.p, n, key0, key1, (uint32_t *)dout.p);
+    if (rc) return rc;
+    RRTB_CUDA(ctx, cudaMemcpyAsync(out4, dout.p, 16 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RRTB_OK;
+}
+
+int rrtb_scatter(rrtb_ctx *ctx, const float *in16, const uint32_t *rnd4, int n, float *out8)
+{
+    if (!ctx || !in16 || !rnd4 || !out8 || n < 0) return RRTB_ERR_INVALID;
+    if (!ctx->has_scene) {
+        ctx->err = "scatter before rrtb_scene_set";
+        return RRTB_ERR_NO_SCENE;
+    }
+    if (n == 0) return RRTB_OK;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf di, dr, dout;
+    HOOK_ALLOC(di, 64 * (size_t)n);
+    HOOK_ALLOC(dr, 16 * (size_t)n);
+    HOOK_ALLOC(dout, 32 * (size_t)n);
+    RRTB_CUDA(ctx, cudaMemcpyAsync(di.p, in16, 64 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    RRTB_CUDA(ctx, cudaMemcpyAsync(dr.p, rnd4, 16 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_scatter(ctx, (const float *)di.p, (const uint32_t *)dr.p, n, (float *)dout.p);
+    if (rc) return rc;
+    RRTB_CUDA(ctx, cudaMemcpyAsync(out8, dout.p, 32 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RRTB_OK;
+}
+
+} // extern "C"

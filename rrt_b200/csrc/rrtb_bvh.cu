@@ -1,0 +1,513 @@
+// rrtb_bvh.cu -- GPU-built LBVH for the rrt hot path (sm_100a).
+//
+// Replaces create_world<<<1,1>>> (rrt.cu:124-174) and the single-thread recursive median-split
+// bvh_node constructor with its O(n^2) dev_sort (bvh.h:65-78,81-159).  Pipeline (all on the device,
+// every stage a grid-wide kernel, no host round trips):
+//
+//   k_prepare      raw scene structs -> 48-byte leaf records, per-primitive AABB (sphere.h:60-64,
+//                  moving_sphere.h:60-66 over the camera shutter, triangle.h:77-87), block partials of
+//                  the centroid bounds
+//   k_bounds       final reduction -> centroid lo, 1/extent, traversal box padding
+//   k_morton       30-bit Morton code of the centroid, 64-bit key = code << 32 | object id
+//   radix sort     4 stable LSD passes of 8 bits over the code (k_hist / k_scan / k_scatter)
+//   k_karras       Karras 2012 internal nodes from the sorted keys (delta = clz64 of key xor)
+//   k_refit        bottom-up boxes, second arrival at a node computes it (fminf/fmaxf: order independent)
+//   k_flatten_*    64-byte two-child nodes with padded boxes + leaf-ordered 48-byte primitive records
+//
+// Every floating-point step that feeds the Morton code uses explicit _rn intrinsics so the codes, the
+// permutation and the topology are BIT-EXACT against oracle/rrt_oracle.c (tests/test_lbvh_parity.py).
+#include "rrtb_internal.h"
+
+#include <math.h>
+#include <stdio.h>
+
+namespace rrtb {
+
+static constexpr int TPB = 256;
+// layout of the small constant block that lives at the end of d_reduce
+struct BuildConsts {
+    float lo[3];
+    float inv[3];
+    float pad;
+    float mag;
+};
+
+__device__ __forceinline__ float warp_min(float v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+__device__ __forceinline__ void unit3_rn(float &x, float &y, float &z)
+{
+    float inv = __fdiv_rn(1.0f, __fsqrt_rn(dot3_rn(x, y, z, x, y, z)));
+    x = __fmul_rn(inv, x);
+    y = __fmul_rn(inv, y);
+    z = __fmul_rn(inv, z);
+}
+
+// One thread per object id.  partial[b*7 + 0..2] = centroid min, 3..5 = centroid max, 6 = max |coordinate|
+__global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__ sph, int ns,
+                                                  const rrtb_msphere *__restrict__ msph, int nms,
+                                                  const rrtb_triangle *__restrict__ tri, int nt, float cam_t0,
+                                                  float cam_t1, float4 *__restrict__ prim, int2 *__restrict__ info,
+                                                  float *__restrict__ prim_box, float *__restrict__ partial)
+{
+    const int n = ns + nms + nt;
+    const int id = blockIdx.x * TPB + threadIdx.x;
+    const float inf = __int_as_float(0x7f800000);
+    float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
+    if (id < n) {
+        float4 a, b = make_float4(0, 0, 0, 0), c = make_float4(0, 0, 0, 0);
+        int mat;
+        if (id < ns) {
+            rrtb_sphere s = sph[id];
+            a = make_float4(s.center[0], s.center[1], s.center[2], s.radius);
+            mat = s.material;
+            for (int k = 0; k < 3; ++k) {
+                mn[k] = __fsub_rn(s.center[k], s.radius);
+                mx[k] = __fadd_rn(s.center[k], s.radius);
+            }
+        }
+        else if (id < ns + nms) {
+            rrtb_msphere m = msph[id - ns];
+            float dt = __fsub_rn(m.time1, m.time0);
+            float k0 = __fdiv_rn(__fsub_rn(cam_t0, m.time0), dt);
+            float k1 = __fdiv_rn(__fsub_rn(cam_t1, m.time0), dt);
+            float dc[3];
+            for (int k = 0; k < 3; ++k) {
+                dc[k] = __fsub_rn(m.center1[k], m.center0[k]);
+                float ca = __fadd_rn(m.center0[k], __fmul_rn(k0, dc[k]));
+                float cb = __fadd_rn(m.center0[k], __fmul_rn(k1, dc[k]));
+                mn[k] = fminf(__fsub_rn(ca, m.radius), __fsub_rn(cb, m.radius));
+                mx[k] = fmaxf(__fadd_rn(ca, m.radius), __fadd_rn(cb, m.radius));
+            }
+            a = make_float4(m.center0[0], m.center0[1], m.center0[2], m.radius);
+            b = make_float4(dc[0], dc[1], dc[2], m.time0);
+            c = make_float4(dt, 0.f, 0.f, 0.f);
+            mat = m.material;
+        }
+        else {
+            rrtb_triangle t = tri[id - ns - nms];
+            float e1[3], e2[3];
+            for (int k = 0; k < 3; ++k) {
+                e1[k] = __fsub_rn(t.v1[k], t.v0[k]);
+                e2[k] = __fsub_rn(t.v2[k], t.v0[k]);
+                mn[k] = fminf(fminf(t.v0[k], t.v1[k]), t.v2[k]);
+                mx[k] = fmaxf(fmaxf(t.v0[k], t.v1[k]), t.v2[k]);
+            }
+            // triangle.h:9-15: unit(cross(unit(v1-v0), unit(v2-v0)))
+            float ax = e1[0], ay = e1[1], az = e1[2], bx = e2[0], by = e2[1], bz = e2[2];
+            unit3_rn(ax, ay, az);
+            unit3_rn(bx, by, bz);
+            float nx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
+            float ny = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
+            float nz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+            unit3_rn(nx, ny, nz);
+            a = make_float4(t.v0[0], t.v0[1], t.v0[2], nx);
+            b = make_float4(e1[0], e1[1], e1[2], ny);
+            c = make_float4(e2[0], e2[1], e2[2], nz);
+            mat = t.material;
+        }
+        prim[3 * id + 0] = a;
+        prim[3 * id + 1] = b;
+        prim[3 * id + 2] = c;
+        info[id] = make_int2(id, mat);
+        for (int k = 0; k < 3; ++k) {
+            prim_box[6 * id + k] = mn[k];
+            prim_box[6 * id + 3 + k] = mx[k];
+        }
+    }
+    // block reduction of centroid bounds and coordinate magnitude
+    float v[7];
+    if (id < n) {
+        float mag = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            float cen = __fmul_rn(0.5f, __fadd_rn(mn[k], mx[k]));
+            v[k] = cen;
+            v[3 + k] = cen;
+            mag = fmaxf(mag, fmaxf(fabsf(mn[k]), fabsf(mx[k])));
+        }
+        v[6] = mag;
+    }
+    else {
+        for (int k = 0; k < 3; ++k) {
+            v[k] = inf;
+            v[3 + k] = -inf;
+        }
+        v[6] = 0.f;
+    }
+    __shared__ float sh[7][TPB / 32];
+    for (int k = 0; k < 7; ++k) {
+        float r = k < 3 ? warp_min(v[k]) : warp_max(v[k]);
+        if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        int k = threadIdx.x;
+        float r = sh[k][0];
+        for (int w = 1; w < TPB / 32; ++w) r = k < 3 ? fminf(r, sh[k][w]) : fmaxf(r, sh[k][w]);
+        partial[blockIdx.x * 7 + k] = r;
+    }
+}
+
+// single block: reduce the per-block partials, derive the Morton normalisation and the box padding
+__global__ void __launch_bounds__(TPB) k_bounds(const float *__restrict__ partial, int nblocks, float cam_mag,
+                                                 BuildConsts *__restrict__ out)
+{
+    const float inf = __int_as_float(0x7f800000);
+    float v[7];
+    for (int k = 0; k < 7; ++k) v[k] = k < 3 ? inf : (k < 6 ? -inf : 0.f);
+    for (int b = threadIdx.x; b < nblocks; b += TPB)
+        for (int k = 0; k < 7; ++k) {
+            float x = partial[b * 7 + k];
+            v[k] = k < 3 ? fminf(v[k], x) : fmaxf(v[k], x);
+        }
+    __shared__ float sh[7][TPB / 32];
+    for (int k = 0; k < 7; ++k) {
+        float r = k < 3 ? warp_min(v[k]) : warp_max(v[k]);
+        if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r[7];
+        for (int k = 0; k < 7; ++k) {
+            r[k] = sh[k][0];
+            for (int w = 1; w < TPB / 32; ++w) r[k] = k < 3 ? fminf(r[k], sh[k][w]) : fmaxf(r[k], sh[k][w]);
+        }
+        for (int k = 0; k < 3; ++k) {
+            float ext = __fsub_rn(r[3 + k], r[k]);
+            out->lo[k] = r[k];
+            out->inv[k] = ext > 0.f ? __fdiv_rn(1.0f, ext) : 0.f;
+        }
+        float mag = fmaxf(r[6], cam_mag);
+        out->mag = mag;
+        out->pad = __fmul_rn(mag, 4.76837158203125e-07f); // 2^-21 * largest coordinate magnitude
+    }
+}
+
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(TPB) k_morton(const float *__restrict__ prim_box, int n,
+                                                 const BuildConsts *__restrict__ bc, uint32_t *__restrict__ morton,
+                                                 uint64_t *__restrict__ keys)
+{
+    int id = blockIdx.x * TPB + threadIdx.x;
+    if (id >= n) return;
+    uint32_t q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float cen = __fmul_rn(0.5f, __fadd_rn(prim_box[6 * id + k], prim_box[6 * id + 3 + k]));
+        float x = __fmul_rn(__fsub_rn(cen, bc->lo[k]), bc->inv[k]);
+        int v = (int)__fmul_rn(x, 1024.0f); // truncation toward zero, as the C cast
+        v = v < 0 ? 0 : (v > 1023 ? 1023 : v);
+        q[k] = (uint32_t)v;
+    }
+    uint32_t code = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
+    morton[id] = code;
+    keys[id] = ((uint64_t)code << 32) | (uint32_t)id;
+}
+
+// ---- stable LSD radix sort, 8 bits per pass ---------------------------------------------------------
+// Each WARP owns a contiguous segment of SEG keys, so the global order of (segment, position) is the
+// input order and stability falls out of processing a segment front to back.
+static constexpr int SEG = 1024;           // keys per warp
+static constexpr int SORT_WARPS = TPB / 32; // warps per block
+
+__global__ void __launch_bounds__(TPB) k_hist(const uint64_t *__restrict__ keys, int n, int shift, int n_seg,
+                                               unsigned int *__restrict__ hist)
+{
+    __shared__ unsigned int sh[SORT_WARPS][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = blockIdx.x * SORT_WARPS + w;
+    for (int d = lane; d < 256; d += 32) sh[w][d] = 0;
+    __syncwarp();
+    if (seg < n_seg) {
+        const int beg = seg * SEG, end = min(beg + SEG, n);
+        for (int i = beg + lane; i < end; i += 32) atomicAdd(&sh[w][(unsigned)(keys[i] >> shift) & 255u], 1u);
+        __syncwarp();
+        for (int d = lane; d < 256; d += 32) hist[d * n_seg + seg] = sh[w][d];
+    }
+}
+
+// exclusive scan of hist[256 * n_seg] (digit-major), single block
+__global__ void __launch_bounds__(1024) k_scan(unsigned int *__restrict__ hist, int total)
+{
+    __shared__ unsigned int warp_sums[32];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < total; base += 1024) {
+        int i = base + threadIdx.x;
+        unsigned int v = i < total ? hist[i] : 0u;
+        unsigned int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            unsigned int s = warp_sums[lane];
+            unsigned int si = s;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned int t = __shfl_up_sync(0xffffffffu, si, o);
+                if (lane >= o) si += t;
+            }
+            warp_sums[lane] = si - s; // exclusive prefix of warp sums
+        }
+        __syncthreads();
+        unsigned int excl = carry + warp_sums[w] + incl - v;
+        if (i < total) hist[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int n,
+                                                  int shift, int n_seg, const unsigned int *__restrict__ hist)
+{
+    __shared__ unsigned int off[SORT_WARPS][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = blockIdx.x * SORT_WARPS + w;
+    if (seg >= n_seg) return;
+    for (int d = lane; d < 256; d += 32) off[w][d] = hist[d * n_seg + seg];
+    __syncwarp();
+    const int beg = seg * SEG, end = min(beg + SEG, n);
+    for (int base = beg; base < end; base += 32) {
+        int i = base + lane;
+        bool valid = i < end;
+        unsigned int active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            uint64_t key = in[i];
+            unsigned int d = (unsigned)(key >> shift) & 255u;
+            unsigned int peers = __match_any_sync(active, d);
+            unsigned int rank = __popc(peers & ((1u << lane) - 1u));
+            unsigned int pos = off[w][d] + rank;
+            out[pos] = key;
+            __syncwarp(active);
+            if (rank == 0) off[w][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- Karras 2012 ------------------------------------------------------------------------------------
+__device__ __forceinline__ int delta_fn(const uint64_t *__restrict__ keys, int n, uint64_t ki, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    return __clzll((long long)(ki ^ keys[j]));
+}
+
+__global__ void __launch_bounds__(TPB) k_karras(const uint64_t *__restrict__ keys, int n, int *__restrict__ left,
+                                                 int *__restrict__ right, int *__restrict__ parent)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    const int ni = n - 1;
+    if (i >= ni) return;
+    const uint64_t ki = keys[i];
+    int d = (delta_fn(keys, n, ki, i + 1) - delta_fn(keys, n, ki, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta_fn(keys, n, ki, i - d);
+    int lmax = 2;
+    while (delta_fn(keys, n, ki, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta_fn(keys, n, ki, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta_fn(keys, n, ki, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta_fn(keys, n, ki, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + (d < 0 ? -1 : 0);
+    int mn = min(i, j), mx = max(i, j);
+    int L = (mn == gamma) ? ~gamma : gamma;
+    int R = (mx == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    left[i] = L;
+    right[i] = R;
+    parent[L >= 0 ? L : (ni + ~L)] = i;
+    parent[R >= 0 ? R : (ni + ~R)] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+// one thread per leaf climbs; the second thread to reach a node computes its box
+__global__ void __launch_bounds__(TPB) k_refit(const uint64_t *__restrict__ keys, int n,
+                                                const int *__restrict__ left, const int *__restrict__ right,
+                                                const int *__restrict__ parent, const float *__restrict__ prim_box,
+                                                float *node_box, int *visit)
+{
+    const int k = blockIdx.x * TPB + threadIdx.x;
+    const int ni = n - 1;
+    if (k >= n) return;
+    int node = parent[ni + k];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&visit[node], 1) == 0) return;
+        __threadfence();
+        const int L = left[node], R = right[node];
+        const volatile float *lb = L >= 0 ? node_box + 6 * L : nullptr;
+        const volatile float *rb = R >= 0 ? node_box + 6 * R : nullptr;
+        float l6[6], r6[6];
+        for (int c = 0; c < 6; ++c) {
+            l6[c] = L >= 0 ? lb[c] : prim_box[6 * (uint32_t)keys[~L] + c];
+            r6[c] = R >= 0 ? rb[c] : prim_box[6 * (uint32_t)keys[~R] + c];
+        }
+        for (int c = 0; c < 3; ++c) {
+            node_box[6 * node + c] = fminf(l6[c], r6[c]);
+            node_box[6 * node + 3 + c] = fmaxf(l6[3 + c], r6[3 + c]);
+        }
+        node = parent[node];
+    }
+}
+
+__device__ __forceinline__ int prim_type(int id, int ns, int nms) { return id < ns ? PRIM_SPHERE : (id < ns + nms ? PRIM_MSPHERE : PRIM_TRIANGLE); }
+
+__global__ void __launch_bounds__(TPB) k_flatten_nodes(const uint64_t *__restrict__ keys, int n, int ns, int nms,
+                                                        const int *__restrict__ left, const int *__restrict__ right,
+                                                        const float *__restrict__ prim_box,
+                                                        const float *__restrict__ node_box,
+                                                        const BuildConsts *__restrict__ bc, float4 *__restrict__ nodes)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    const int ni = n - 1;
+    const float pad = bc->pad;
+    if (n == 1) { // degenerate tree: both children of the root are the only leaf (as bvh.h:116-118 does)
+        if (i == 0) {
+            const float *b = prim_box;
+            float lo0 = __fsub_rn(b[0], pad), lo1 = __fsub_rn(b[1], pad), lo2 = __fsub_rn(b[2], pad);
+            float hi0 = __fadd_rn(b[3], pad), hi1 = __fadd_rn(b[4], pad), hi2 = __fadd_rn(b[5], pad);
+            int enc = ~((0 << 2) | prim_type(0, ns, nms));
+            nodes[0] = make_float4(lo0, lo1, lo2, hi0);
+            nodes[1] = make_float4(hi1, hi2, lo0, lo1);
+            nodes[2] = make_float4(lo2, hi0, hi1, hi2);
+            nodes[3] = make_float4(__int_as_float(enc), __int_as_float(enc), 0.f, 0.f);
+        }
+        return;
+    }
+    if (i >= ni) return;
+    int ref[2] = {left[i], right[i]};
+    float bx[2][6];
+    int enc[2];
+    for (int c = 0; c < 2; ++c) {
+        const float *b;
+        if (ref[c] >= 0) {
+            b = node_box + 6 * ref[c];
+            enc[c] = ref[c];
+        }
+        else {
+            int slot = ~ref[c];
+            int id = (int)(uint32_t)keys[slot];
+            b = prim_box + 6 * id;
+            enc[c] = ~((slot << 2) | prim_type(id, ns, nms));
+        }
+        for (int k = 0; k < 3; ++k) {
+            bx[c][k] = __fsub_rn(b[k], pad);
+            bx[c][3 + k] = __fadd_rn(b[3 + k], pad);
+        }
+    }
+    nodes[4 * i + 0] = make_float4(bx[0][0], bx[0][1], bx[0][2], bx[0][3]);
+    nodes[4 * i + 1] = make_float4(bx[0][4], bx[0][5], bx[1][0], bx[1][1]);
+    nodes[4 * i + 2] = make_float4(bx[1][2], bx[1][3], bx[1][4], bx[1][5]);
+    nodes[4 * i + 3] = make_float4(__int_as_float(enc[0]), __int_as_float(enc[1]), 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(TPB) k_flatten_leaves(const uint64_t *__restrict__ keys, int n,
+                                                         const float4 *__restrict__ prim, const int2 *__restrict__ info,
+                                                         float4 *__restrict__ leaves, int2 *__restrict__ leaf_info)
+{
+    const int k = blockIdx.x * TPB + threadIdx.x;
+    if (k >= n) return;
+    const int id = (int)(uint32_t)keys[k];
+    leaves[3 * k + 0] = prim[3 * id + 0];
+    leaves[3 * k + 1] = prim[3 * id + 1];
+    leaves[3 * k + 2] = prim[3 * id + 2];
+    leaf_info[k] = info[id];
+}
+
+// exposed to rrtb_api.cu (scene upload): raw struct arrays are staged by the caller
+int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_msphere *d_msph, const rrtb_triangle *d_tri)
+{
+    const int n = ctx->n_prims;
+    const int ns = ctx->n_spheres, nms = ctx->n_mspheres, nt = ctx->n_triangles;
+    const int nb = (n + TPB - 1) / TPB;
+    cudaStream_t st = ctx->stream;
+    BuildConsts *bc = (BuildConsts *)(ctx->d_reduce + (size_t)nb * 7);
+
+    k_prepare<<<nb, TPB, 0, st>>>(d_sph, ns, d_msph, nms, d_tri, nt, ctx->cam.time0, ctx->cam.time1, ctx->d_prim,
+                                  ctx->d_prim_info, ctx->d_prim_box, ctx->d_reduce);
+    float cam_mag = 0.f;
+    for (int k = 0; k < 3; ++k) cam_mag = fmaxf(cam_mag, fabsf(ctx->cam.origin[k]) + ctx->cam.lens_radius);
+    k_bounds<<<1, TPB, 0, st>>>(ctx->d_reduce, nb, cam_mag, bc);
+    k_morton<<<nb, TPB, 0, st>>>(ctx->d_prim_box, n, bc, ctx->d_morton, ctx->d_keys);
+    RRTB_CUDA(ctx, cudaGetLastError());
+
+    // radix sort on the 30-bit code held in key bits 32..61
+    const int n_seg = (n + SEG - 1) / SEG;
+    const int sort_blocks = (n_seg + SORT_WARPS - 1) / SORT_WARPS;
+    uint64_t *src = ctx->d_keys, *dst = ctx->d_keys_tmp;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 32 + 8 * pass;
+        k_hist<<<sort_blocks, TPB, 0, st>>>(src, n, shift, n_seg, ctx->d_hist);
+        k_scan<<<1, 1024, 0, st>>>(ctx->d_hist, 256 * n_seg);
+        k_scatter<<<sort_blocks, TPB, 0, st>>>(src, dst, n, shift, n_seg, ctx->d_hist);
+        uint64_t *t = src;
+        src = dst;
+        dst = t;
+    }
+    RRTB_CUDA(ctx, cudaGetLastError());
+    // 4 passes: result is back in d_keys (src == d_keys)
+
+    if (n > 1) {
+        const int nbi = (n - 1 + TPB - 1) / TPB;
+        RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_visit, 0, sizeof(int) * (size_t)(n - 1), st));
+        k_karras<<<nbi, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left, ctx->d_right, ctx->d_parent);
+        k_refit<<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_prim_box,
+                                    ctx->d_node_box, ctx->d_visit);
+    }
+    else {
+        int m1 = -1;
+        RRTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_parent, &m1, sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    const int nbn = (max(n - 1, 1) + TPB - 1) / TPB;
+    k_flatten_nodes<<<nbn, TPB, 0, st>>>(ctx->d_keys, n, ns, nms, ctx->d_left, ctx->d_right, ctx->d_prim_box,
+                                         ctx->d_node_box, bc, ctx->d_nodes);
+    k_flatten_leaves<<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_prim, ctx->d_prim_info, ctx->d_leaves,
+                                         ctx->d_leaf_info);
+    RRTB_CUDA(ctx, cudaGetLastError());
+    return RRTB_OK;
+}
+
+void free_scene(rrtb_ctx *ctx)
+{
+    auto F = [](auto *&p) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    };
+    F(ctx->d_prim); F(ctx->d_prim_info); F(ctx->d_materials); F(ctx->d_material_type); F(ctx->d_prim_box);
+    F(ctx->d_morton); F(ctx->d_keys); F(ctx->d_keys_tmp); F(ctx->d_left); F(ctx->d_right); F(ctx->d_parent);
+    F(ctx->d_node_box); F(ctx->d_visit); F(ctx->d_nodes); F(ctx->d_leaves); F(ctx->d_leaf_info); F(ctx->d_reduce);
+    F(ctx->d_hist);
+    ctx->has_scene = false;
+}
+
+} // namespace rrtb

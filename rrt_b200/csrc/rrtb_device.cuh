@@ -1,0 +1,520 @@
+// rrtb_device.cuh -- device-side math of the B200 path-tracing core (sm_100a).
+//
+// Everything a ray needs between "generate" and "accumulate": counter-based RNG, primary-ray
+// generation, slab / sphere / moving-sphere / triangle tests, hit record, material scatter.
+// Replaces (file:line under /root/reference):
+//   curand XORWOW + wrappers        rrt.cu:81-89, rtweekend.h:80-91   -> Philox4x32-10, stateless
+//   camera::get_ray                 camera.h:31-38, rrt.cu:112-114
+//   aabb::hit                       aabb.h:18-93                      -> 6 FFMA + FMNMX, no divides
+//   sphere::hit / moving_sphere::hit sphere.h:33-58, moving_sphere.h:27-58
+//   triangle::hit                   triangle.h:35-75
+//   hit_record::set_face_normal     hittable.h:16-20
+//   lambertian/metal/dielectric::scatter material.h:21-32,48-57,76-109 -> type switch, no vtable
+//   reflect / refract               vec3.h:156-164
+//
+// Rounding discipline: functions whose results are compared BIT-EXACTLY with the CPU oracle
+// (oracle/rrt_oracle.c) are written with explicit round-to-nearest intrinsics (__fmaf_rn, __fmul_rn,
+// __fadd_rn, __dmul_rn, __fma_rn ...) which nvcc never contracts or reassociates.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rrtb {
+
+// ---- scene as the kernels see it -----------------------------------------------------------------
+// Leaf record: 3 x float4 (48 B) per primitive, in LEAF ORDER (Morton order for the LBVH, object-id
+// order for the flat scan):
+//   sphere         a = (c.xyz, r)
+//   moving sphere  a = (c0.xyz, r)   b = (c1-c0 .xyz, t0)   c = (t1-t0, -, -, -)
+//   triangle       a = (v0.xyz, n.x) b = (e1.xyz, n.y)      c = (e2.xyz, n.z)    n = unit face normal
+// leaf_info[k] = (object id, material index)
+// BVH node: 4 x float4 (64 B): padded boxes of both children + child refs
+//   n0 = (L.min.xyz, L.max.x)  n1 = (L.max.y, L.max.z, R.min.x, R.min.y)  n2 = (R.min.z, R.max.xyz)
+//   n3 = (bits(left ref), bits(right ref), -, -)
+// child ref >= 0: internal node index;  < 0: leaf, ~ref = (leaf slot << 2) | type
+enum : int { PRIM_SPHERE = 0, PRIM_MSPHERE = 1, PRIM_TRIANGLE = 2 };
+
+struct DeviceScene {
+    const float4 *nodes;     // [4 * max(n-1,1)]
+    const float4 *leaves;    // [3 * n]   leaf order
+    const int2 *leaf_info;   // [n]
+    const float4 *flat_leaves; // [3 * n]  object-id order (scan mode)
+    const int2 *flat_info;   // [n]
+    const float4 *materials; // [nm] (albedo.xyz, param)
+    const int *material_type;// [nm]
+    int n_prims, n_spheres, n_mspheres, n_triangles;
+    int use_bvh;
+};
+
+struct DeviceCamera { // rrtb_camera, by value in kernel params (constant bank)
+    float origin[3], llc[3], horizontal[3], vertical[3], u[3], v[3], w[3];
+    float lens_radius, time0, time1;
+};
+
+struct Ray {
+    float ox, oy, oz, dx, dy, dz, tm;
+};
+
+struct TravCounters { // per-lane work counters of the counting build (V_box, V_sph, V_msph, V_tri)
+    unsigned long long box, sph, msph, tri;
+};
+
+struct Hit {
+    float t;
+    int ref; // encoded leaf ref ((slot << 2) | type), -1 = miss
+    int obj; // object id (valid only after a tie was resolved or after finish)
+};
+
+// ---- Philox4x32-10 -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ float u01(uint32_t x) { return __fmul_rn((float)(x >> 8), 5.9604644775390625e-08f); }
+
+// (cos, sin)(2*pi*(u - 1/2)): exact quadrant reduction + fixed FMA polynomials (bit-exact vs oracle)
+__device__ __forceinline__ void sincos2pi(float u, float &co, float &si)
+{
+    float x = __fadd_rn(u, -0.5f);
+    float qf = rintf(__fmul_rn(x, 4.0f));
+    float r = __fmaf_rn(qf, -0.25f, x);
+    float a = __fmul_rn(r, 6.283185307179586f);
+    float a2 = __fmul_rn(a, a);
+    float sp = __fmaf_rn(a2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = __fmaf_rn(a2, sp, -1.6666654611e-1f);
+    float sn = __fmaf_rn(__fmul_rn(a, a2), sp, a);
+    float cp = __fmaf_rn(a2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = __fmaf_rn(a2, cp, 4.166664568298827e-2f);
+    cp = __fmaf_rn(a2, cp, -0.5f);
+    float cs = __fmaf_rn(a2, cp, 1.0f);
+    int q = (int)qf & 3;
+    co = (q & 1) ? sn : cs;
+    si = (q & 1) ? cs : sn;
+    if (q == 1 || q == 2) co = -co;
+    if (q >= 2) si = -si;
+}
+
+// ---- primary rays: rrt.cu:112-114 + camera.h:31-38 ------------------------------------------------------
+__device__ __forceinline__ Ray camera_ray(const DeviceCamera &cam, int W, int H, int pixel, int sample, uint2 key)
+{
+    uint4 b0 = philox4x32_10(make_uint4((uint32_t)pixel, (uint32_t)sample, 0u, 0u), key);
+    int j = pixel / W, i = pixel - j * W;
+    float u = __fdiv_rn(__fadd_rn((float)i, u01(b0.x)), (float)(W - 1));
+    float v = __fdiv_rn(__fadd_rn((float)j, u01(b0.y)), (float)(H - 1));
+    float ofx = 0.f, ofy = 0.f, ofz = 0.f;
+    if (cam.lens_radius > 0.0f) {
+        float r = __fmul_rn(__fsqrt_rn(u01(b0.z)), cam.lens_radius);
+        float c, s;
+        sincos2pi(u01(b0.w), c, s);
+        float rdx = __fmul_rn(r, c), rdy = __fmul_rn(r, s);
+        ofx = __fmaf_rn(cam.v[0], rdy, __fmul_rn(cam.u[0], rdx));
+        ofy = __fmaf_rn(cam.v[1], rdy, __fmul_rn(cam.u[1], rdx));
+        ofz = __fmaf_rn(cam.v[2], rdy, __fmul_rn(cam.u[2], rdx));
+    }
+    Ray r;
+    r.ox = __fadd_rn(cam.origin[0], ofx);
+    r.oy = __fadd_rn(cam.origin[1], ofy);
+    r.oz = __fadd_rn(cam.origin[2], ofz);
+    r.dx = __fsub_rn(__fsub_rn(__fmaf_rn(v, cam.vertical[0], __fmaf_rn(u, cam.horizontal[0], cam.llc[0])), cam.origin[0]), ofx);
+    r.dy = __fsub_rn(__fsub_rn(__fmaf_rn(v, cam.vertical[1], __fmaf_rn(u, cam.horizontal[1], cam.llc[1])), cam.origin[1]), ofy);
+    r.dz = __fsub_rn(__fsub_rn(__fmaf_rn(v, cam.vertical[2], __fmaf_rn(u, cam.horizontal[2], cam.llc[2])), cam.origin[2]), ofz);
+    r.tm = cam.time0;
+    if (cam.time0 != cam.time1) {
+        uint4 b1 = philox4x32_10(make_uint4((uint32_t)pixel, (uint32_t)sample, 1u, 0u), key);
+        r.tm = __fmaf_rn(__fsub_rn(cam.time1, cam.time0), u01(b1.x), cam.time0);
+    }
+    return r;
+}
+
+// ---- per-ray precomputation ------------------------------------------------------------------------------
+struct RayPre {
+    float ix, iy, iz;    // 1/d  (correctly rounded)
+    float oox, ooy, ooz; // -o/d
+    double a;            // d.d in double
+    float af;
+};
+
+__device__ __forceinline__ RayPre ray_pre(const Ray &r)
+{
+    RayPre p;
+    p.ix = __frcp_rn(r.dx);
+    p.iy = __frcp_rn(r.dy);
+    p.iz = __frcp_rn(r.dz);
+    p.oox = -__fmul_rn(r.ox, p.ix);
+    p.ooy = -__fmul_rn(r.oy, p.iy);
+    p.ooz = -__fmul_rn(r.oz, p.iz);
+    double dx = r.dx, dy = r.dy, dz = r.dz;
+    p.a = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+    p.af = __double2float_rn(p.a);
+    return p;
+}
+
+// slab test on one (already padded) box; inclusive; returns entry distance in tn
+__device__ __forceinline__ bool box_hit(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
+                                        const RayPre &p, float t_min, float t_max, float &tn)
+{
+    float x0 = __fmaf_rn(bminx, p.ix, p.oox), x1 = __fmaf_rn(bmaxx, p.ix, p.oox);
+    float y0 = __fmaf_rn(bminy, p.iy, p.ooy), y1 = __fmaf_rn(bmaxy, p.iy, p.ooy);
+    float z0 = __fmaf_rn(bminz, p.iz, p.ooz), z1 = __fmaf_rn(bmaxz, p.iz, p.ooz);
+    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_min));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
+    return tn <= tf;
+}
+
+// ---- primitive tests (bit-exact vs oracle sphere_roots / triangle_t) ---------------------------------------
+// sphere.h:33-58: nearest root in [t_min, t_max], inclusive.  oc, half_b, c and the discriminant in
+// double (the cancellation-prone part), roots in float via the cancellation-free pair q/a, c/q.
+__device__ __forceinline__ bool sphere_test(const Ray &r, const RayPre &p, float cx, float cy, float cz, float rad,
+                                            float t_min, float t_max, float &t_out)
+{
+    double ocx = __dsub_rn((double)r.ox, (double)cx);
+    double ocy = __dsub_rn((double)r.oy, (double)cy);
+    double ocz = __dsub_rn((double)r.oz, (double)cz);
+    double dx = r.dx, dy = r.dy, dz = r.dz;
+    double hb = __fma_rn(ocz, dz, __fma_rn(ocy, dy, __dmul_rn(ocx, dx)));
+    double rr = rad;
+    double cc = __fma_rn(-rr, rr, __fma_rn(ocz, ocz, __fma_rn(ocy, ocy, __dmul_rn(ocx, ocx))));
+    double disc = __fma_rn(-p.a, cc, __dmul_rn(hb, hb));
+    if (disc < 0.0) return false;
+    float sq = __fsqrt_rn(__double2float_rn(disc));
+    float hbf = __double2float_rn(hb), ccf = __double2float_rn(cc);
+    float q = -__fadd_rn(hbf, copysignf(sq, hbf));
+    float r0 = __fdiv_rn(q, p.af), r1 = __fdiv_rn(ccf, q);
+    float tn = fminf(r0, r1), tf = fmaxf(r0, r1);
+    float root = tn;
+    if (!(root >= t_min && root <= t_max)) {
+        root = tf;
+        if (!(root >= t_min && root <= t_max)) return false;
+    }
+    t_out = root;
+    return true;
+}
+
+// moving_sphere.h:27-30
+__device__ __forceinline__ void msphere_center(float4 a, float4 b, float4 c, float time, float &cx, float &cy, float &cz)
+{
+    float k = __fdiv_rn(__fsub_rn(time, b.w), c.x);
+    cx = __fmaf_rn(k, b.x, a.x);
+    cy = __fmaf_rn(k, b.y, a.y);
+    cz = __fmaf_rn(k, b.z, a.z);
+}
+
+__device__ __forceinline__ double dcross(double a, double b, double c, double d)
+{
+    return __fma_rn(a, b, -__dmul_rn(c, d));
+}
+
+// triangle.h:35-75: Moeller-Trumbore, numerators in double, division-free barycentric tests, exclusive range
+__device__ __forceinline__ bool triangle_test(const Ray &r, float4 A, float4 B, float4 C, float t_min, float t_max,
+                                              float &t_out)
+{
+    const double EPS = (double)1e-7f;
+    double e1x = B.x, e1y = B.y, e1z = B.z, e2x = C.x, e2y = C.y, e2z = C.z;
+    double dx = r.dx, dy = r.dy, dz = r.dz;
+    double hx = dcross(dy, e2z, dz, e2y), hy = dcross(dz, e2x, dx, e2z), hz = dcross(dx, e2y, dy, e2x);
+    double det = __fma_rn(e1z, hz, __fma_rn(e1y, hy, __dmul_rn(e1x, hx)));
+    if (det > -EPS && det < EPS) return false;
+    double sx = __dsub_rn((double)r.ox, (double)A.x), sy = __dsub_rn((double)r.oy, (double)A.y),
+           sz = __dsub_rn((double)r.oz, (double)A.z);
+    double un = __fma_rn(sz, hz, __fma_rn(sy, hy, __dmul_rn(sx, hx)));
+    double qx = dcross(sy, e1z, sz, e1y), qy = dcross(sz, e1x, sx, e1z), qz = dcross(sx, e1y, sy, e1x);
+    double vn = __fma_rn(dz, qz, __fma_rn(dy, qy, __dmul_rn(dx, qx)));
+    if (det > 0.0) {
+        if (un < 0.0 || un > det || vn < 0.0 || __dadd_rn(un, vn) > det) return false;
+    }
+    else {
+        if (un > 0.0 || un < det || vn > 0.0 || __dadd_rn(un, vn) < det) return false;
+    }
+    double tn = __fma_rn(e2z, qz, __fma_rn(e2y, qy, __dmul_rn(e2x, qx)));
+    float t = __fdiv_rn(__double2float_rn(tn), __double2float_rn(det));
+    if (t > 1e-7f && t > t_min && t < t_max) {
+        t_out = t;
+        return true;
+    }
+    return false;
+}
+
+// Order-independent form of the flat scan's tie rule (hittable_list.h:102-114 with the inclusive sphere
+// range and exclusive triangle range): at exactly equal t the LAST sphere-like object in id order wins,
+// else the FIRST triangle.
+__device__ __forceinline__ bool candidate_wins(float t, int type, int obj, float bt, int btype, int bobj)
+{
+    if (bobj < 0) return true;
+    if (t < bt) return true;
+    if (t > bt) return false;
+    bool ct = type == PRIM_TRIANGLE, bt_tri = btype == PRIM_TRIANGLE;
+    if (ct != bt_tri) return !ct;
+    return ct ? (obj < bobj) : (obj > bobj);
+}
+
+// Test leaf `slot` (type known) and update the running closest hit.
+template <bool COUNT>
+__device__ __forceinline__ void leaf_test(const float4 *__restrict__ leaves, const int2 *__restrict__ info, int slot,
+                                          int type, const Ray &r, const RayPre &p, float t_min, Hit &best,
+                                          TravCounters &cnt)
+{
+    if (COUNT) {
+        if (type == PRIM_SPHERE) ++cnt.sph;
+        else if (type == PRIM_MSPHERE) ++cnt.msph;
+        else ++cnt.tri;
+    }
+    float4 a = __ldg(leaves + 3 * slot);
+    float t;
+    bool h;
+    if (type == PRIM_SPHERE) {
+        h = sphere_test(r, p, a.x, a.y, a.z, a.w, t_min, best.t, t);
+    }
+    else if (type == PRIM_MSPHERE) {
+        float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+        float cx, cy, cz;
+        msphere_center(a, b, c, r.tm, cx, cy, cz);
+        h = sphere_test(r, p, cx, cy, cz, a.w, t_min, best.t, t);
+    }
+    else {
+        float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+        h = triangle_test(r, a, b, c, t_min, best.t, t);
+    }
+    if (!h) return;
+    if (best.ref >= 0 && t == best.t) { // exact tie: resolve by object id (rare path)
+        int obj = __ldg(&info[slot]).x;
+        int bobj = __ldg(&info[best.ref >> 2]).x;
+        if (!candidate_wins(t, type, obj, best.t, best.ref & 3, bobj)) return;
+    }
+    best.t = t;
+    best.ref = (slot << 2) | type;
+}
+
+// ---- closest hit: flat scan (hittable_list.h:95-117) ------------------------------------------------------
+template <bool COUNT>
+__device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, const RayPre &p, float t_min,
+                                            TravCounters &cnt)
+{
+    Hit best;
+    best.t = __int_as_float(0x7f800000);
+    best.ref = -1;
+    best.obj = -1;
+    const int n0 = s.n_spheres, n1 = n0 + s.n_mspheres, n = s.n_prims;
+    for (int k = 0; k < n; ++k) {
+        int type = k < n0 ? PRIM_SPHERE : (k < n1 ? PRIM_MSPHERE : PRIM_TRIANGLE);
+        leaf_test<COUNT>(s.flat_leaves, s.flat_info, k, type, r, p, t_min, best, cnt);
+    }
+    return best;
+}
+
+// ---- closest hit: LBVH traversal (replaces bvh_node::hit recursion, bvh.h:167-175) -------------------------
+// Iterative, near-child-first, one 64-byte node fetch tests both children.  STACK entries live in
+// local memory (L1-resident); depth of a 30-bit-Morton + index-tiebreak Karras tree is <= 62.
+#define RRTB_STACK 64
+
+template <bool COUNT>
+__device__ __forceinline__ Hit closest_bvh(const DeviceScene &s, const Ray &r, const RayPre &p, float t_min,
+                                           TravCounters &cnt)
+{
+    Hit best;
+    best.t = __int_as_float(0x7f800000);
+    best.ref = -1;
+    best.obj = -1;
+    int stack[RRTB_STACK];
+    int sp = 0;
+    int cur = 0;
+    const float4 *__restrict__ nodes = s.nodes;
+    while (true) {
+        float4 n0 = __ldg(nodes + 4 * cur), n1 = __ldg(nodes + 4 * cur + 1), n2 = __ldg(nodes + 4 * cur + 2),
+               n3 = __ldg(nodes + 4 * cur + 3);
+        float tl, tr;
+        if (COUNT) cnt.box += 2;
+        bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, p, t_min, best.t, tl);
+        bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, p, t_min, best.t, tr);
+        int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+        if (hl && cl < 0) {
+            leaf_test<COUNT>(s.leaves, s.leaf_info, (~cl) >> 2, (~cl) & 3, r, p, t_min, best, cnt);
+            hl = false;
+        }
+        if (hr && cr < 0) {
+            leaf_test<COUNT>(s.leaves, s.leaf_info, (~cr) >> 2, (~cr) & 3, r, p, t_min, best, cnt);
+            hr = false;
+        }
+        if (hl && hr) {
+            bool left_first = tl <= tr;
+            int nearc = left_first ? cl : cr, farc = left_first ? cr : cl;
+            stack[sp++] = farc;
+            cur = nearc;
+        }
+        else if (hl) {
+            cur = cl;
+        }
+        else if (hr) {
+            cur = cr;
+        }
+        else {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    return best;
+}
+
+// ---- hit record: sphere.h:51-55, moving_sphere.h:51-55, triangle.h:62-66, hittable.h:16-20 ----------------
+struct HitRecord {
+    float px, py, pz, nx, ny, nz;
+    bool front;
+    int obj, mat;
+};
+
+__device__ __forceinline__ HitRecord hit_record(const float4 *__restrict__ leaves, const int2 *__restrict__ info,
+                                                const Ray &r, const Hit &h)
+{
+    HitRecord rec;
+    int slot = h.ref >> 2, type = h.ref & 3;
+    rec.px = __fmaf_rn(h.t, r.dx, r.ox);
+    rec.py = __fmaf_rn(h.t, r.dy, r.oy);
+    rec.pz = __fmaf_rn(h.t, r.dz, r.oz);
+    float4 a = __ldg(leaves + 3 * slot);
+    if (type == PRIM_TRIANGLE) {
+        float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+        rec.nx = a.w;
+        rec.ny = b.w;
+        rec.nz = c.w;
+    }
+    else {
+        float cx = a.x, cy = a.y, cz = a.z;
+        if (type == PRIM_MSPHERE) {
+            float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+            msphere_center(a, b, c, r.tm, cx, cy, cz);
+        }
+        float inv = __frcp_rn(a.w);
+        rec.nx = __fmul_rn(inv, __fsub_rn(rec.px, cx));
+        rec.ny = __fmul_rn(inv, __fsub_rn(rec.py, cy));
+        rec.nz = __fmul_rn(inv, __fsub_rn(rec.pz, cz));
+    }
+    float dn = __fadd_rn(__fadd_rn(__fmul_rn(r.dx, rec.nx), __fmul_rn(r.dy, rec.ny)), __fmul_rn(r.dz, rec.nz));
+    rec.front = dn < 0.0f;
+    if (!rec.front) {
+        rec.nx = -rec.nx;
+        rec.ny = -rec.ny;
+        rec.nz = -rec.nz;
+    }
+    int2 inf = __ldg(&info[slot]);
+    rec.obj = inf.x;
+    rec.mat = inf.y;
+    return rec;
+}
+
+// ---- materials ------------------------------------------------------------------------------------------
+// One Philox block per bounce (see oracle/rrt_oracle.c "materials" for the stream layout).  The scatter
+// code may use fast reciprocal-sqrt: its results are compared with the oracle to a tolerance, not bitwise.
+__device__ __forceinline__ void sample_unit_sphere(float x0, float x1, float &ux, float &uy, float &uz)
+{
+    float z = fmaf(-2.0f, x0, 1.0f);
+    float rr = sqrtf(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
+    float c, s;
+    sincos2pi(x1, c, s);
+    ux = rr * c;
+    uy = rr * s;
+    uz = z;
+}
+
+// returns true if the path continues; (dx,dy,dz) = scattered direction, (ar,ag,ab) = attenuation
+__device__ __forceinline__ bool scatter(int mtype, float4 m, const Ray &r, const HitRecord &rec, uint4 rnd, float &dx,
+                                        float &dy, float &dz, float &ar, float &ag, float &ab)
+{
+    const float nx = rec.nx, ny = rec.ny, nz = rec.nz;
+    if (mtype == 0) { // lambertian, material.h:21-32
+        float ux, uy, uz;
+        sample_unit_sphere(u01(rnd.x), u01(rnd.y), ux, uy, uz);
+        dx = nx + ux;
+        dy = ny + uy;
+        dz = nz + uz;
+        if (fabsf(dx) < 1e-8f && fabsf(dy) < 1e-8f && fabsf(dz) < 1e-8f) {
+            dx = nx;
+            dy = ny;
+            dz = nz;
+        }
+        ar = m.x;
+        ag = m.y;
+        ab = m.z;
+        return true;
+    }
+    float inv = rsqrtf(fmaf(r.dz, r.dz, fmaf(r.dy, r.dy, r.dx * r.dx)));
+    float udx = r.dx * inv, udy = r.dy * inv, udz = r.dz * inv;
+    float dn = fmaf(udz, nz, fmaf(udy, ny, udx * nx));
+    if (mtype == 1) { // metal, material.h:48-57
+        float k = -2.0f * dn;
+        dx = fmaf(k, nx, udx);
+        dy = fmaf(k, ny, udy);
+        dz = fmaf(k, nz, udz);
+        float fuzz = fminf(m.w, 1.0f);
+        if (fuzz > 0.0f) {
+            float ux, uy, uz;
+            sample_unit_sphere(u01(rnd.x), u01(rnd.y), ux, uy, uz);
+            float ra = u01(rnd.z);
+            float rb = (float)(rnd.w >> 16) * 1.52587890625e-05f;
+            float rc = (float)(rnd.w & 0xFFFFu) * 1.52587890625e-05f;
+            float rad = fmaxf(ra, fmaxf(rb, rc)) * fuzz;
+            dx = fmaf(rad, ux, dx);
+            dy = fmaf(rad, uy, dy);
+            dz = fmaf(rad, uz, dz);
+        }
+        ar = m.x;
+        ag = m.y;
+        ab = m.z;
+        return fmaf(dz, nz, fmaf(dy, ny, dx * nx)) > 0.0f;
+    }
+    // dielectric, material.h:76-109 + vec3.h:158-164
+    float ir = m.w;
+    float eta = rec.front ? __frcp_rn(ir) : ir;
+    float cos_t = fminf(-dn, 1.0f);
+    float sin_t = sqrtf(fmaxf(0.0f, fmaf(-cos_t, cos_t, 1.0f)));
+    bool cannot = eta * sin_t > 1.0f;
+    float r0 = __fdividef(1.0f - eta, 1.0f + eta);
+    r0 = r0 * r0;
+    float om = 1.0f - cos_t;
+    float om2 = om * om;
+    float refl_p = fmaf(1.0f - r0, om2 * om2 * om, r0);
+    if (cannot || refl_p > u01(rnd.x)) {
+        float k = -2.0f * dn;
+        dx = fmaf(k, nx, udx);
+        dy = fmaf(k, ny, udy);
+        dz = fmaf(k, nz, udz);
+    }
+    else {
+        float px = eta * fmaf(cos_t, nx, udx), py = eta * fmaf(cos_t, ny, udy), pz = eta * fmaf(cos_t, nz, udz);
+        float k = -sqrtf(fabsf(1.0f - fmaf(pz, pz, fmaf(py, py, px * px))));
+        dx = fmaf(k, nx, px);
+        dy = fmaf(k, ny, py);
+        dz = fmaf(k, nz, pz);
+    }
+    ar = ag = ab = 1.0f;
+    return true;
+}
+
+// sky, rrt.cu:68-75
+__device__ __forceinline__ void sky(const Ray &r, float &cr, float &cg, float &cb)
+{
+    float inv = rsqrtf(fmaf(r.dz, r.dz, fmaf(r.dy, r.dy, r.dx * r.dx)));
+    float t = 0.5f * fmaf(r.dy, inv, 1.0f);
+    float w = 1.0f - t;
+    cr = fmaf(t, 0.5f, w);
+    cg = fmaf(t, 0.7f, w);
+    cb = fmaf(t, 1.0f, w);
+}
+
+// radiance -> 2^40 fixed point (integer accumulation is associative => bit-reproducible images under
+// any scheduling, sharding or reduction order)
+__device__ __forceinline__ unsigned long long to_fixed(float x)
+{
+    if (!(x > 0.0f)) return 0ull;
+    x = fminf(x, 1048576.0f);
+    return __double2ull_rn((double)x * 1099511627776.0);
+}
+
+} // namespace rrtb

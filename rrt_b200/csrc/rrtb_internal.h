@@ -1,0 +1,83 @@
+// rrtb_internal.h -- host-side context shared by the translation units of librrtb200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rrtb.h"
+#include "rrtb_device.cuh"
+
+struct rrtb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    std::string err;
+
+    // scene (host copies kept for camera updates / introspection)
+    bool has_scene = false;
+    rrtb_camera cam{};
+    int n_materials = 0, n_spheres = 0, n_mspheres = 0, n_triangles = 0, n_prims = 0;
+    int use_bvh = 1;
+    double seconds_build = 0.0;
+
+    // device: canonical primitive arrays (object-id order)
+    float4 *d_prim = nullptr;       // [3*n] leaf records in object-id order (== flat_leaves)
+    int2 *d_prim_info = nullptr;    // [n]   (object id, material)
+    float4 *d_materials = nullptr;  // [nm]
+    int *d_material_type = nullptr; // [nm]
+    // device: canonical LBVH arrays (rrtb_bvh_download)
+    float *d_prim_box = nullptr;    // [6n]
+    uint32_t *d_morton = nullptr;   // [n]
+    uint64_t *d_keys = nullptr;     // [n] sorted (code << 32 | id)
+    uint64_t *d_keys_tmp = nullptr; // [n]
+    int *d_left = nullptr, *d_right = nullptr; // [n-1]
+    int *d_parent = nullptr;        // [2n-1]
+    float *d_node_box = nullptr;    // [6(n-1)]
+    int *d_visit = nullptr;         // [n-1]
+    // device: traversal structures
+    float4 *d_nodes = nullptr;      // [4*max(n-1,1)]
+    float4 *d_leaves = nullptr;     // [3n] leaf order
+    int2 *d_leaf_info = nullptr;    // [n]
+    // scratch
+    float *d_reduce = nullptr;      // block partials + build constants
+    unsigned int *d_hist = nullptr; // radix histograms
+    size_t hist_elems = 0;
+    unsigned long long *d_counters = nullptr; // [0] work queue head, [1] ray counter
+    unsigned long long *d_accum = nullptr;    // host-path accumulator (3*W*H)
+    float *d_rgb = nullptr;                   // host-path float framebuffer
+    size_t accum_elems = 0;
+};
+
+namespace rrtb {
+
+// error helper: records the reference-style message (rrt.cu:31-40) and returns RRTB_ERR_CUDA
+int cuda_fail(rrtb_ctx *ctx, cudaError_t e, const char *expr, const char *file, int line);
+
+#define RRTB_CUDA(ctx, expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) return ::rrtb::cuda_fail((ctx), _e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// rrtb_bvh.cu
+int build_acceleration(rrtb_ctx *ctx);
+void free_scene(rrtb_ctx *ctx);
+
+// rrtb_render.cu
+DeviceScene device_scene(const rrtb_ctx *ctx);
+DeviceCamera device_camera(const rrtb_camera &c);
+int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum, rrtb_stats *stats);
+int launch_resolve(rrtb_ctx *ctx, const uint64_t *d_accum, float *d_out, size_t n);
+int launch_accumulate(rrtb_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t n);
+int launch_trace(rrtb_ctx *ctx, const float *d_rays7, int n, float t_min, int mode, int32_t *d_id, float *d_t,
+                 float *d_rec7);
+int launch_camera_rays(rrtb_ctx *ctx, const rrtb_render_params *p, const int32_t *d_pix, int n, int sample,
+                       float *d_rays7);
+int launch_philox(rrtb_ctx *ctx, const uint32_t *d_ctr, int n, uint32_t k0, uint32_t k1, uint32_t *d_out);
+int launch_probe(rrtb_ctx *ctx, int mix, double *lane_instr_per_s);
+int launch_scatter(rrtb_ctx *ctx, const float *d_in16, const uint32_t *d_rnd4, int n, float *d_out8);
+
+} // namespace rrtb

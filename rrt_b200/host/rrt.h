@@ -1,0 +1,77 @@
+// rrt.h -- the renderer seam of rogerallen/rrt (reference rrt.h:14-48), re-implemented as a thin C++
+// shim over the C ABI of librrtb200.so (include/rrtb.h).  Same constructor shape as the reference's
+// CUDA build (threads_x/threads_y accepted, see below), same `render(scene*) -> fb` contract:
+// fb[j*W+i] = SUM over samples of RGB radiance, j = 0 the bottom scanline, owned by the Rrt object.
+#ifndef RRTB_HOST_RRT_H
+#define RRTB_HOST_RRT_H
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "rrtb.h"
+
+struct vec3 { // layout-compatible with the reference's float vec3 (vec3.h:21-81): 3 x FP_T
+    float e[3];
+    float x() const { return e[0]; }
+    float y() const { return e[1]; }
+    float z() const { return e[2]; }
+};
+
+// Failure convention of the reference (rrt.cu:31-40): message on stderr, exit(99).
+inline void rrtb_check(int rc, rrtb_ctx *ctx, const char *what)
+{
+    if (rc == RRTB_OK) return;
+    std::fprintf(stderr, "%s failed (%d): %s\n", what, rc, rrtb_last_error(ctx));
+    std::exit(99);
+}
+
+class Rrt {
+  public:
+    // threads_x/threads_y (-tx/-ty, main.cpp:94-104) tuned the reference's one-thread-per-pixel grid;
+    // the persistent kernel sizes its own grid (SMs x resident blocks), so they are accepted and unused.
+    Rrt(int image_width, int image_height, int samples_per_pixel, int max_depth, bool use_bvh, int threads_x = 8,
+        int threads_y = 8, int device = 0, unsigned long long seed = 1984, int rank = 0, int world = 1)
+        : image_width(image_width), image_height(image_height), samples_per_pixel(samples_per_pixel),
+          max_depth(max_depth), num_threads_x(threads_x), num_threads_y(threads_y), bvh(use_bvh), seed(seed),
+          rank(rank), world(world), ctx(nullptr)
+    {
+        rrtb_check(rrtb_create(&ctx, device), nullptr, "rrtb_create");
+        stats = rrtb_stats();
+    }
+    ~Rrt() { rrtb_destroy(ctx); }
+    Rrt(const Rrt &) = delete;
+    Rrt &operator=(const Rrt &) = delete;
+
+    vec3 *render(const rrtb_scene *the_scene)
+    {
+        rrtb_check(rrtb_scene_upload(ctx, the_scene, bvh ? 1 : 0), ctx, "rrtb_scene_upload");
+        fb.resize((size_t)image_width * image_height);
+        rrtb_render_params p{};
+        p.width = image_width;
+        p.height = image_height;
+        p.spp = samples_per_pixel;
+        p.max_depth = max_depth;
+        p.seed = seed;
+        p.rank = rank;
+        p.world = world;
+        p.shard_mode = RRTB_SHARD_TILES;
+        p.count_rays = 1;
+        rrtb_check(rrtb_render(ctx, &p, &fb[0].e[0], &stats), ctx, "rrtb_render");
+        return fb.data();
+    }
+
+    rrtb_stats stats;
+    rrtb_ctx *context() { return ctx; }
+
+  private:
+    int image_width, image_height, samples_per_pixel, max_depth;
+    int num_threads_x, num_threads_y;
+    bool bvh;
+    unsigned long long seed;
+    int rank, world;
+    rrtb_ctx *ctx;
+    std::vector<vec3> fb;
+};
+
+#endif

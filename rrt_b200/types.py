@@ -63,6 +63,11 @@ class Stats(C.Structure):
         ("seconds_resolve", C.c_double),
         ("rays", C.c_uint64),
         ("paths", C.c_uint64),
+        ("box_tests", C.c_uint64),
+        ("sphere_tests", C.c_uint64),
+        ("msphere_tests", C.c_uint64),
+        ("triangle_tests", C.c_uint64),
+        ("hits", C.c_uint64),
         ("kernel_launches", C.c_int32),
         ("reserved", C.c_int32),
     ]
