@@ -112,6 +112,12 @@ int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam);
  * (rrt.cu:42-79). */
 
 enum { RRTB_SHARD_TILES = 0, RRTB_SHARD_SAMPLES = 1 };
+/* kernel scheduling (same image bit for bit either way; DESIGN.md "scheduling shoot-out"):
+ *   RRTB_SCHED_AUTO    the library's default (currently the pool scheduler)
+ *   RRTB_SCHED_SIMPLE  persistent threads, one path per lane, the warp syncs at every segment
+ *   RRTB_SCHED_POOL    persistent threads, per-warp pool of paths in shared memory: lanes refill as soon as
+ *                      their traversal ends, shading runs 32 wide (rrtb_render_pool.cuh) */
+enum { RRTB_SCHED_AUTO = 0, RRTB_SCHED_SIMPLE = 1, RRTB_SCHED_POOL = 2 };
 
 typedef struct rrtb_render_params {
     int32_t width, height;     /* -w -h   (main.cpp:56-57) */
@@ -121,6 +127,8 @@ typedef struct rrtb_render_params {
     int32_t rank, world;       /* this context renders shard `rank` of `world` (1 GPU: 0,1) */
     int32_t shard_mode;        /* RRTB_SHARD_TILES: interleaved 8x4-pixel tiles; RRTB_SHARD_SAMPLES: sample ranges */
     int32_t count_rays;        /* != 0: also count ray segments (stats.rays); same image either way */
+    int32_t scheduler;         /* RRTB_SCHED_* */
+    int32_t reserved;
 } rrtb_render_params;
 
 typedef struct rrtb_stats {

@@ -729,6 +729,13 @@ void orc_path(const orc_scene *s, const orc_bvh *bvh, int W, int H, int pixel, i
 {
     float ray7[7];
     orc_camera_ray(&s->cam, W, H, pixel, sample, seed, ray7);
+    orc_radiance(s, bvh, ray7, pixel, sample, max_depth, seed, rgb, cnt);
+}
+
+/* ray_color (rrt.cu:42-79) for an explicit primary ray; (pixel, sample) only key the bounce RNG. */
+void orc_radiance(const orc_scene *s, const orc_bvh *bvh, const float *ray7, int pixel, int sample, int max_depth,
+                  uint64_t seed, float *rgb, orc_counters *cnt)
+{
     f3 o = ld3(ray7), d = ld3(ray7 + 3);
     float time = ray7[6];
     f3 thr = F3(1.f, 1.f, 1.f);

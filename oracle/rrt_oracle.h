@@ -78,6 +78,9 @@ void orc_scatter(const orc_scene *s, const float *in16, const uint32_t *rnd4, in
  * bvh may be NULL (flat scan). Pixels with (tile_index % world) != rank are left 0 when world > 1. */
 void orc_render(const orc_scene *s, const orc_bvh *bvh, int W, int H, int spp, int max_depth, uint64_t seed,
                 int rank, int world, int shard_mode, float *out_rgb, uint64_t *out_fixed, orc_counters *cnt);
+/* ray_color for an explicit primary ray ((pixel, sample) only key the bounce RNG) */
+void orc_radiance(const orc_scene *s, const orc_bvh *bvh, const float *ray7, int pixel, int sample, int max_depth,
+                  uint64_t seed, float *rgb, orc_counters *cnt);
 /* one camera path; returns radiance in rgb[3] */
 void orc_path(const orc_scene *s, const orc_bvh *bvh, int W, int H, int pixel, int sample, int max_depth,
               uint64_t seed, float *rgb, orc_counters *cnt);

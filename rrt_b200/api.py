@@ -165,13 +165,13 @@ class Context:
 
     # -- render -----------------------------------------------------------------------------------------
     @staticmethod
-    def params(width, height, spp, max_depth=50, seed=1984, rank=0, world=1, shard_mode=0, count_rays=False):
+    def params(width, height, spp, max_depth=50, seed=1984, rank=0, world=1, shard_mode=0, count_rays=False, scheduler=0):
         return RenderParams(int(width), int(height), int(spp), int(max_depth), int(seed), int(rank), int(world),
-                            int(shard_mode), 1 if count_rays else 0)
+                            int(shard_mode), 1 if count_rays else 0, int(scheduler), 0)
 
-    def render(self, width, height, spp, max_depth=50, seed=1984, rank=0, world=1, shard_mode=0, count_rays=False, out=None):
+    def render(self, width, height, spp, max_depth=50, seed=1984, rank=0, world=1, shard_mode=0, count_rays=False, out=None, scheduler=0):
         """Host-buffer path (what Rrt::render returns): float32 [H, W, 3] SUMS, row 0 = bottom scanline."""
-        p = self.params(width, height, spp, max_depth, seed, rank, world, shard_mode, count_rays)
+        p = self.params(width, height, spp, max_depth, seed, rank, world, shard_mode, count_rays, scheduler)
         if out is None:
             out = np.empty((height, width, 3), np.float32)
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == 3 * width * height

@@ -158,6 +158,20 @@ __device__ __forceinline__ RayPre ray_pre(const Ray &r)
     return p;
 }
 
+// sm_100a 3-input min/max (PTX ISA 8.6, SASS FMNMX3): a slab test needs 10 alu-pipe ops instead of 12
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 // slab test on one (already padded) box; inclusive; returns entry distance in tn
 __device__ __forceinline__ bool box_hit(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
                                         const RayPre &p, float t_min, float t_max, float &tn)
@@ -165,8 +179,8 @@ __device__ __forceinline__ bool box_hit(float bminx, float bminy, float bminz, f
     float x0 = __fmaf_rn(bminx, p.ix, p.oox), x1 = __fmaf_rn(bmaxx, p.ix, p.oox);
     float y0 = __fmaf_rn(bminy, p.iy, p.ooy), y1 = __fmaf_rn(bmaxy, p.iy, p.ooy);
     float z0 = __fmaf_rn(bminz, p.iz, p.ooz), z1 = __fmaf_rn(bmaxz, p.iz, p.ooz);
-    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_min));
-    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
+    tn = fmaxf(fmax3(fminf(x0, x1), fminf(y0, y1), fminf(z0, z1)), t_min);
+    float tf = fminf(fmin3(fmaxf(x0, x1), fmaxf(y0, y1), fmaxf(z0, z1)), t_max);
     return tn <= tf;
 }
 
@@ -311,9 +325,51 @@ __device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, 
 }
 
 // ---- closest hit: LBVH traversal (replaces bvh_node::hit recursion, bvh.h:167-175) -------------------------
-// Iterative, near-child-first, one 64-byte node fetch tests both children.  STACK entries live in
-// local memory (L1-resident); depth of a 30-bit-Morton + index-tiebreak Karras tree is <= 62.
+// Iterative and STEP-WISE so that a warp-level scheduler can interleave it with other work:
+//   cur >= 0          internal node to visit  -> node_step: one 64-byte node fetch tests both children,
+//                     near child first, far child pushed
+//   cur <  0          a leaf reference        -> leaf_step: exact primitive test, then pop
+//   cur == TRAV_DONE  traversal finished
+// Stack entries live in local memory (L1-resident); the depth of a 30-bit-Morton + index-tiebreak Karras
+// tree is <= 62.
 #define RRTB_STACK 64
+#define TRAV_DONE ((int)0x80000000)
+
+template <bool COUNT>
+__device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, const RayPre &p, float t_min, float t_max,
+                                          int &cur, int &sp, int *stack, TravCounters &cnt)
+{
+    float4 n0 = __ldg(nodes + 4 * cur), n1 = __ldg(nodes + 4 * cur + 1), n2 = __ldg(nodes + 4 * cur + 2),
+           n3 = __ldg(nodes + 4 * cur + 3);
+    float tl, tr;
+    if (COUNT) cnt.box += 2;
+    bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, p, t_min, t_max, tl);
+    bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, p, t_min, t_max, tr);
+    int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+    if (hl && hr) {
+        bool left_first = tl <= tr;
+        stack[sp++] = left_first ? cr : cl;
+        cur = left_first ? cl : cr;
+    }
+    else if (hl) {
+        cur = cl;
+    }
+    else if (hr) {
+        cur = cr;
+    }
+    else {
+        cur = sp > 0 ? stack[--sp] : TRAV_DONE;
+    }
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void leaf_step(const float4 *__restrict__ leaves, const int2 *__restrict__ info, const Ray &r,
+                                          const RayPre &p, float t_min, Hit &best, int &cur, int &sp, int *stack,
+                                          TravCounters &cnt)
+{
+    leaf_test<COUNT>(leaves, info, (~cur) >> 2, (~cur) & 3, r, p, t_min, best, cnt);
+    cur = sp > 0 ? stack[--sp] : TRAV_DONE;
+}
 
 template <bool COUNT>
 __device__ __forceinline__ Hit closest_bvh(const DeviceScene &s, const Ray &r, const RayPre &p, float t_min,
@@ -326,39 +382,9 @@ __device__ __forceinline__ Hit closest_bvh(const DeviceScene &s, const Ray &r, c
     int stack[RRTB_STACK];
     int sp = 0;
     int cur = 0;
-    const float4 *__restrict__ nodes = s.nodes;
-    while (true) {
-        float4 n0 = __ldg(nodes + 4 * cur), n1 = __ldg(nodes + 4 * cur + 1), n2 = __ldg(nodes + 4 * cur + 2),
-               n3 = __ldg(nodes + 4 * cur + 3);
-        float tl, tr;
-        if (COUNT) cnt.box += 2;
-        bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, p, t_min, best.t, tl);
-        bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, p, t_min, best.t, tr);
-        int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
-        if (hl && cl < 0) {
-            leaf_test<COUNT>(s.leaves, s.leaf_info, (~cl) >> 2, (~cl) & 3, r, p, t_min, best, cnt);
-            hl = false;
-        }
-        if (hr && cr < 0) {
-            leaf_test<COUNT>(s.leaves, s.leaf_info, (~cr) >> 2, (~cr) & 3, r, p, t_min, best, cnt);
-            hr = false;
-        }
-        if (hl && hr) {
-            bool left_first = tl <= tr;
-            int nearc = left_first ? cl : cr, farc = left_first ? cr : cl;
-            stack[sp++] = farc;
-            cur = nearc;
-        }
-        else if (hl) {
-            cur = cl;
-        }
-        else if (hr) {
-            cur = cr;
-        }
-        else {
-            if (sp == 0) break;
-            cur = stack[--sp];
-        }
+    while (cur != TRAV_DONE) {
+        if (cur >= 0) node_step<COUNT>(s.nodes, p, t_min, best.t, cur, sp, stack, cnt);
+        else leaf_step<COUNT>(s.leaves, s.leaf_info, r, p, t_min, best, cur, sp, stack, cnt);
     }
     return best;
 }

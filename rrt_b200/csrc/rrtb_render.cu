@@ -22,6 +22,7 @@
 #include "rrtb_internal.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace rrtb {
 
@@ -40,6 +41,8 @@ struct RenderArgs {
     int n_chunks;        // ceil(n_local_samples / CHUNK)
     unsigned long long n_items; // n_local_tiles * n_chunks * 32
     unsigned long long *accum;  // 3*W*H fixed-point sums
+    int th_fetch, th_shade, th_leaf; // pool-scheduler thresholds (lanes)
+    int step_iters;                  // node visits per scheduling round
     unsigned long long *queue;  // [0] queue head, [1] rays, [2] box tests, [3] sphere, [4] msphere, [5] triangle tests, [6] hits
 };
 
@@ -170,6 +173,10 @@ __global__ void __launch_bounds__(RENDER_TPB, 2) k_render(const RenderArgs a)
         }
     }
 }
+
+} // namespace rrtb
+#include "rrtb_render_pool.cuh"
+namespace rrtb {
 
 __global__ void k_resolve(const unsigned long long *__restrict__ acc, float *__restrict__ out, size_t n)
 {
@@ -339,18 +346,41 @@ DeviceCamera device_camera(const rrtb_camera &c)
     return d;
 }
 
+template <typename K>
+static int launch_persistent(rrtb_ctx *ctx, K kernel, const RenderArgs &args, int *blocks_out)
+{
+    int per_sm = 0;
+    RRTB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RENDER_TPB, 0));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long want = (args.n_items + RENDER_TPB - 1) / RENDER_TPB;
+    int blocks = ctx->sm_count * per_sm; // persistent: one wave, a multiple of the SM count
+    if ((unsigned long long)blocks > want) blocks = (int)(want ? want : 1);
+    kernel<<<blocks, RENDER_TPB, 0, ctx->stream>>>(args);
+    *blocks_out = blocks;
+    return RRTB_OK;
+}
+
+template <typename K>
+static int launch_pool(rrtb_ctx *ctx, K kernel, const RenderArgs &args, int *blocks_out)
+{
+    const int smem = (int)(sizeof(WarpPool) * POOL_WARPS);
+    RRTB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    RRTB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RENDER_TPB, smem));
+    if (per_sm < 1) per_sm = 1;
+    // persistent: one wave; every warp needs at least a pool's worth of paths to be worth launching
+    unsigned long long want = (args.n_items + (unsigned long long)POOL * POOL_WARPS - 1) / ((unsigned long long)POOL * POOL_WARPS);
+    int blocks = ctx->sm_count * per_sm;
+    if ((unsigned long long)blocks > want) blocks = (int)(want ? want : 1);
+    kernel<<<blocks, RENDER_TPB, smem, ctx->stream>>>(args);
+    *blocks_out = blocks;
+    return RRTB_OK;
+}
+
 template <bool B, bool C>
 static int launch_render_t(rrtb_ctx *ctx, const RenderArgs &args, int *blocks_out)
 {
-    int per_sm = 0;
-    RRTB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render<B, C>, RENDER_TPB, 0));
-    if (per_sm < 1) per_sm = 1;
-    unsigned long long want = (args.n_items + RENDER_TPB - 1) / RENDER_TPB;
-    int blocks = ctx->sm_count * per_sm;
-    if ((unsigned long long)blocks > want) blocks = (int)(want ? want : 1);
-    k_render<B, C><<<blocks, RENDER_TPB, 0, ctx->stream>>>(args);
-    *blocks_out = blocks;
-    return RRTB_OK;
+    return launch_persistent(ctx, k_render<B, C>, args, blocks_out);
 }
 
 int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum, rrtb_stats *stats)
@@ -381,7 +411,18 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     if (a.n_local_samples < 0) a.n_local_samples = 0;
     a.n_chunks = (a.n_local_samples + CHUNK - 1) / CHUNK;
     a.n_items = (unsigned long long)a.n_local_tiles * (unsigned long long)a.n_chunks * 32ull;
+    const bool use_pool = ctx->use_bvh != 0 && p->scheduler != RRTB_SCHED_SIMPLE;
+    if (use_pool) // the pool scheduler hands out single camera paths: (tile, sample, pixel in tile)
+        a.n_items = (unsigned long long)a.n_local_tiles * (unsigned long long)a.n_local_samples * 32ull;
     a.accum = (unsigned long long *)d_accum;
+    a.th_fetch = 16;
+    a.th_shade = 32;
+    a.th_leaf = 8;
+    a.step_iters = 4;
+    if (const char *e = getenv("RRTB_STEP_ITERS")) a.step_iters = atoi(e);
+    if (const char *e = getenv("RRTB_TH_FETCH")) a.th_fetch = atoi(e); // tuning aids
+    if (const char *e = getenv("RRTB_TH_SHADE")) a.th_shade = atoi(e);
+    if (const char *e = getenv("RRTB_TH_LEAF")) a.th_leaf = atoi(e);
     a.queue = ctx->d_counters;
 
     RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -391,7 +432,10 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     if (a.n_items > 0) {
         const bool bvh = ctx->use_bvh != 0, cnt = p->count_rays != 0;
         int rc;
-        if (bvh && cnt) rc = launch_render_t<true, true>(ctx, a, &blocks);
+        if (bvh && p->scheduler != RRTB_SCHED_SIMPLE) {
+            rc = cnt ? launch_pool(ctx, k_render_pool<true>, a, &blocks) : launch_pool(ctx, k_render_pool<false>, a, &blocks);
+        }
+        else if (bvh && cnt) rc = launch_render_t<true, true>(ctx, a, &blocks);
         else if (bvh) rc = launch_render_t<true, false>(ctx, a, &blocks);
         else if (cnt) rc = launch_render_t<false, true>(ctx, a, &blocks);
         else rc = launch_render_t<false, false>(ctx, a, &blocks);

@@ -9,6 +9,7 @@ import numpy as np
 
 LAMBERTIAN, METAL, DIELECTRIC = 0, 1, 2
 SHARD_TILES, SHARD_SAMPLES = 0, 1
+SCHED_AUTO, SCHED_SIMPLE, SCHED_POOL = 0, 1, 2
 
 camera_dtype = np.dtype(
     [
@@ -51,6 +52,8 @@ class RenderParams(C.Structure):
         ("world", C.c_int32),
         ("shard_mode", C.c_int32),
         ("count_rays", C.c_int32),
+        ("scheduler", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
