@@ -454,7 +454,7 @@ orc_bvh *orc_bvh_build(const orc_scene *s)
         }
     }
     for (int k = 0; k < 3; ++k) mag = fmaxf(mag, fabsf(s->cam.origin[k]) + s->cam.lens_radius);
-    b->pad = mag * 4.76837158203125e-07f; /* 2^-21 * largest coordinate magnitude (DESIGN.md "box padding") */
+    b->pad = mag * 9.5367431640625e-07f; /* 2^-20 * largest coordinate magnitude (DESIGN.md "box padding") */
 
     float inv[3];
     for (int k = 0; k < 3; ++k) {

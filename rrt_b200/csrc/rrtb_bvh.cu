@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(TPB) k_bounds(const float *__restrict__ partia
         }
         float mag = fmaxf(r[6], cam_mag);
         out->mag = mag;
-        out->pad = __fmul_rn(mag, 4.76837158203125e-07f); // 2^-21 * largest coordinate magnitude
+        out->pad = __fmul_rn(mag, 9.5367431640625e-07f); // 2^-20 * largest coordinate magnitude
     }
 }
 

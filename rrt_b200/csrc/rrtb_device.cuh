@@ -104,10 +104,10 @@ __device__ __forceinline__ void sincos2pi(float u, float &co, float &si)
 }
 
 // ---- primary rays: rrt.cu:112-114 + camera.h:31-38 ------------------------------------------------------
-__device__ __forceinline__ Ray camera_ray(const DeviceCamera &cam, int W, int H, int pixel, int sample, uint2 key)
+__device__ __forceinline__ Ray camera_ray(const DeviceCamera &cam, int W, int H, int i, int j, int sample, uint2 key)
 {
+    const int pixel = j * W + i;
     uint4 b0 = philox4x32_10(make_uint4((uint32_t)pixel, (uint32_t)sample, 0u, 0u), key);
-    int j = pixel / W, i = pixel - j * W;
     float u = __fdiv_rn(__fadd_rn((float)i, u01(b0.x)), (float)(W - 1));
     float v = __fdiv_rn(__fadd_rn((float)j, u01(b0.y)), (float)(H - 1));
     float ofx = 0.f, ofy = 0.f, ofz = 0.f;
@@ -136,25 +136,30 @@ __device__ __forceinline__ Ray camera_ray(const DeviceCamera &cam, int W, int H,
 }
 
 // ---- per-ray precomputation ------------------------------------------------------------------------------
+// The slab test only has to be CONSERVATIVE (boxes are padded by 2^-20 * scene magnitude at flatten time,
+// which covers the rounding of the FMA form and of the approximate reciprocal), so 1/d is one MUFU.RCP.
+// Exactness lives in the leaf tests.
 struct RayPre {
-    float ix, iy, iz;    // 1/d  (correctly rounded)
+    float ix, iy, iz;    // ~1/d
     float oox, ooy, ooz; // -o/d
-    double a;            // d.d in double
-    float af;
 };
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 __device__ __forceinline__ RayPre ray_pre(const Ray &r)
 {
     RayPre p;
-    p.ix = __frcp_rn(r.dx);
-    p.iy = __frcp_rn(r.dy);
-    p.iz = __frcp_rn(r.dz);
-    p.oox = -__fmul_rn(r.ox, p.ix);
-    p.ooy = -__fmul_rn(r.oy, p.iy);
-    p.ooz = -__fmul_rn(r.oz, p.iz);
-    double dx = r.dx, dy = r.dy, dz = r.dz;
-    p.a = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
-    p.af = __double2float_rn(p.a);
+    p.ix = rcp_approx(r.dx);
+    p.iy = rcp_approx(r.dy);
+    p.iz = rcp_approx(r.dz);
+    p.oox = -r.ox * p.ix;
+    p.ooy = -r.oy * p.iy;
+    p.ooz = -r.oz * p.iz;
     return p;
 }
 
@@ -194,15 +199,16 @@ __device__ __forceinline__ bool sphere_test(const Ray &r, const RayPre &p, float
     double ocy = __dsub_rn((double)r.oy, (double)cy);
     double ocz = __dsub_rn((double)r.oz, (double)cz);
     double dx = r.dx, dy = r.dy, dz = r.dz;
+    double a = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
     double hb = __fma_rn(ocz, dz, __fma_rn(ocy, dy, __dmul_rn(ocx, dx)));
     double rr = rad;
     double cc = __fma_rn(-rr, rr, __fma_rn(ocz, ocz, __fma_rn(ocy, ocy, __dmul_rn(ocx, ocx))));
-    double disc = __fma_rn(-p.a, cc, __dmul_rn(hb, hb));
+    double disc = __fma_rn(-a, cc, __dmul_rn(hb, hb));
     if (disc < 0.0) return false;
     float sq = __fsqrt_rn(__double2float_rn(disc));
     float hbf = __double2float_rn(hb), ccf = __double2float_rn(cc);
     float q = -__fadd_rn(hbf, copysignf(sq, hbf));
-    float r0 = __fdiv_rn(q, p.af), r1 = __fdiv_rn(ccf, q);
+    float r0 = __fdiv_rn(q, __double2float_rn(a)), r1 = __fdiv_rn(ccf, q);
     float tn = fminf(r0, r1), tf = fmaxf(r0, r1);
     float root = tn;
     if (!(root >= t_min && root <= t_max)) {

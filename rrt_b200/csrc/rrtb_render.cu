@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 2) k_render(const RenderArgs a)
         if (active) {
             if (!in_path) { // ---- generate: rrt.cu:112-114 + camera.h:31-38
                 int sample = a.shard_mode == RRTB_SHARD_SAMPLES ? ls * a.world + a.rank : ls;
-                ray = camera_ray(a.cam, a.W, a.H, pixel, sample, a.key);
+                ray = camera_ray(a.cam, a.W, a.H, pixel % a.W, pixel / a.W, sample, a.key);
                 thr_r = thr_g = thr_b = 1.f;
                 bounce = 0;
                 in_path = true;
@@ -229,7 +229,7 @@ __global__ void k_camera_rays(const DeviceCamera cam, int W, int H, uint2 key, c
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Ray r = camera_ray(cam, W, H, pix[i], sample, key);
+    Ray r = camera_ray(cam, W, H, pix[i] % W, pix[i] / W, sample, key);
     rays7[7 * i + 0] = r.ox; rays7[7 * i + 1] = r.oy; rays7[7 * i + 2] = r.oz;
     rays7[7 * i + 3] = r.dx; rays7[7 * i + 4] = r.dy; rays7[7 * i + 5] = r.dz;
     rays7[7 * i + 6] = r.tm;

@@ -176,21 +176,42 @@ __global__ void __launch_bounds__(RENDER_TPB, 3) k_render_pool(const RenderArgs 
                 if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(new_mask));
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (base + (unsigned long long)__popc(new_mask) >= a.n_items) queue_empty = true;
+                // decode (local tile, local sample) of the first item once per warp (64-bit division), the
+                // other lanes are at most one (tile, sample) group further on
+                const unsigned long long ts0 = base >> 5;
+                int ls0 = 0, ltile0 = 0;
+                if ((int)lane == leader) {
+                    ltile0 = (int)(ts0 / (unsigned long long)a.n_local_samples);
+                    ls0 = (int)(ts0 - (unsigned long long)ltile0 * (unsigned long long)a.n_local_samples);
+                }
+                ls0 = __shfl_sync(0xffffffffu, ls0, leader);
+                ltile0 = __shfl_sync(0xffffffffu, ltile0, leader);
                 if (want_new) {
                     const unsigned long long item = base + __popc(new_mask & lt_mask);
                     if (item < a.n_items) {
                         // item = (local_tile * n_local_samples + local_sample) * 32 + pixel_in_tile
                         const unsigned pit = (unsigned)(item & 31ull);
-                        const unsigned long long ts = item >> 5;
-                        const int ls = (int)(ts % (unsigned long long)a.n_local_samples);
-                        const int ltile = (int)(ts / (unsigned long long)a.n_local_samples);
+                        int ls = ls0 + (int)((item >> 5) - ts0), ltile = ltile0;
+                        if (ls >= a.n_local_samples) {
+                            ls -= a.n_local_samples;
+                            ++ltile;
+                        }
                         const int tile = a.shard_mode == RRTB_SHARD_TILES ? ltile * a.world + a.rank : ltile;
-                        const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
+                        int ty = (int)__fdividef((float)tile, (float)a.tiles_x); // float estimate, off by <= 1 ...
+                        int tx = tile - ty * a.tiles_x;
+                        if (tx < 0) { // ... corrected exactly in integers
+                            --ty;
+                            tx += a.tiles_x;
+                        }
+                        else if (tx >= a.tiles_x) {
+                            ++ty;
+                            tx -= a.tiles_x;
+                        }
                         const int i = tx * 8 + (int)(pit & 7u), j = ty * 4 + (int)(pit >> 3);
                         if (i < a.W && j < a.H) { // else: padding pixel of an edge tile -> slot stays fresh
                             pixel = j * a.W + i;
                             sample = a.shard_mode == RRTB_SHARD_SAMPLES ? ls * a.world + a.rank : ls;
-                            Ray r = camera_ray(a.cam, a.W, a.H, pixel, sample, a.key);
+                            Ray r = camera_ray(a.cam, a.W, a.H, i, j, sample, a.key);
                             wp.ox[sl] = r.ox; wp.oy[sl] = r.oy; wp.oz[sl] = r.oz;
                             wp.dx[sl] = r.dx; wp.dy[sl] = r.dy; wp.dz[sl] = r.dz;
                             wp.tm[sl] = r.tm;

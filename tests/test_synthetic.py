@@ -1,0 +1,89 @@
+"""Scaled-up synthetic scenes (BASELINE.json configs[4] family).  CPU part: the generated text is in the
+reference grammar -- the reference's own parser reads it and agrees with ours.  GPU part: the multi-segment
+radix sort / LBVH at tens of thousands of primitives, bit-exact vs the oracle; LBVH hits == flat-scan hits."""
+import numpy as np
+import pytest
+
+from oracle_lib import Oracle, RefScene, have_ref, pinhole_rays
+
+
+@pytest.fixture(scope="module")
+def synth_small(tmp_path_factory, built_lib):
+    from rrt_b200 import Scene
+    from rrt_b200.synthetic import write_synthetic_scene
+
+    p = tmp_path_factory.mktemp("synth") / "synth_small.txt"
+    write_synthetic_scene(str(p), n_spheres=3000, ico_level=3, grid=3)  # 3004 spheres + 11520 triangles
+    return str(p), Scene.from_file(str(p), 640, 360)
+
+
+def test_generated_text_is_reference_grammar(synth_small):
+    path, scene = synth_small
+    c = scene.counts()
+    assert (c["spheres"], c["triangles"], c["objs"], c["obj_insts"], c["materials"]) == (3004, 9 * 1280, 1, 9, 3004)
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    ref = RefScene(path, 640, 360, "f").arrays()
+    for k in ("camera", "materials", "spheres", "mspheres", "triangles"):
+        assert getattr(scene.arrays, k).tobytes() == getattr(ref, k).tobytes(), k
+
+
+def test_oracle_lbvh_on_synthetic(synth_small):
+    path, scene = synth_small
+    orc = Oracle(scene.arrays)
+    rays = pinhole_rays(scene.arrays, 640, 360, step=8)
+    a = orc.trace(rays, 0.001, "scan")
+    b = orc.trace(rays, 0.001, "bvh")
+    assert np.array_equal(a[0], b[0]) and a[1].tobytes() == b[1].tobytes()
+    assert (a[0] >= 0).mean() > 0.5
+
+
+@pytest.mark.gpu
+def test_gpu_lbvh_multi_segment_sort(ctx, synth_small):
+    """14 524 primitives: 15 radix-sort segments, 4 passes -- codes, order, topology and boxes bit-exact."""
+    path, scene = synth_small
+    ctx.set_scene(scene, use_bvh=True)
+    got, want = ctx.bvh_arrays(), Oracle(scene.arrays).bvh_arrays()
+    for k in ("morton", "perm", "left", "right", "parent"):
+        assert np.array_equal(got[k], want[k]), k
+    for k in ("prim_box", "node_box"):
+        assert got[k].tobytes() == want[k].tobytes(), k
+
+
+@pytest.mark.gpu
+def test_gpu_synthetic_hits_and_render(ctx, synth_small):
+    path, scene = synth_small
+    ctx.set_scene(scene, use_bvh=True)
+    rays = pinhole_rays(scene.arrays, 640, 360, step=2)
+    i_b, t_b = ctx.trace(rays, 0.001, "bvh")
+    o_i, o_t = Oracle(scene.arrays).trace(rays, 0.001, "bvh")
+    assert np.array_equal(i_b, o_i) and t_b.tobytes() == o_t.tobytes()
+    sub = rays[::16]
+    i_s, t_s = ctx.trace(sub, 0.001, "scan")
+    assert np.array_equal(i_s, i_b[::16]) and t_s.tobytes() == t_b[::16].tobytes()
+    # both schedulers render the same image bit for bit
+    a, sa = ctx.render(160, 90, 4, 50, seed=5, scheduler=1, count_rays=True)
+    b, sb = ctx.render(160, 90, 4, 50, seed=5, scheduler=2, count_rays=True)
+    assert a.tobytes() == b.tobytes() and sa["rays"] == sb["rays"]
+
+
+@pytest.mark.gpu
+@pytest.mark.slow
+def test_gpu_large_scene_builds_and_traces(ctx, tmp_path):
+    """~270 k primitives (level-4 icosphere x 49 + 20 k spheres): LBVH parity vs the oracle at scale."""
+    from rrt_b200 import Scene
+    from rrt_b200.synthetic import write_synthetic_scene
+
+    p = tmp_path / "synth_mid.txt"
+    write_synthetic_scene(str(p), n_spheres=20000, ico_level=4, grid=7)
+    scene = Scene.from_file(str(p), 960, 540)
+    assert scene.counts()["triangles"] == 49 * 5120
+    ctx.set_scene(scene, use_bvh=True)
+    got, want = ctx.bvh_arrays(), Oracle(scene.arrays).bvh_arrays()
+    for k in ("morton", "perm", "left", "right", "parent"):
+        assert np.array_equal(got[k], want[k]), k
+    assert got["node_box"].tobytes() == want["node_box"].tobytes()
+    rays = pinhole_rays(scene.arrays, 960, 540, step=3)
+    i_b, t_b = ctx.trace(rays, 0.001, "bvh")
+    o_i, o_t = Oracle(scene.arrays).trace(rays, 0.001, "bvh")
+    assert np.array_equal(i_b, o_i) and t_b.tobytes() == o_t.tobytes()

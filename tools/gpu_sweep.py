@@ -24,6 +24,6 @@ def run(tag, sched, env=None):
     print("%-28s %8.2f ms  %8.1f Mrays/s  same=%s" % (tag, best * 1e3, rays / best / 1e6, same), flush=True)
 run("simple", 1)
 run("pool default", 2)
-for it in (1, 2, 3, 4, 6, 8, 12):
-    for tl in (4, 8, 12):
-        run("pool iters=%d tl=%d" % (it, tl), 2, {"RRTB_STEP_ITERS": it, "RRTB_TH_LEAF": tl})
+for tf in (1, 2, 4, 8, 12, 16, 24):
+    for it in (2, 4):
+        run("pool tf=%d iters=%d" % (tf, it), 2, {"RRTB_TH_FETCH": tf, "RRTB_STEP_ITERS": it})
