@@ -359,6 +359,12 @@ def main():
         kern_rays_per_s = (cst["rays"] if world == 1 else tot["rays"] / world) / kern_s
         achieved = kern_rays_per_s * wr  # lane-instr / s, per GPU
         peak = max(probe["ffma"], probe["ffma_fmnmx_mix"])  # the issue-rate ceiling: 1 warp-instr / clk / SMSP
+        traffic = None  # dram bytes per launch of the render kernel, from the committed ncu --set full capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+                traffic = json.load(f)["traffic_bytes_per_launch"] if (spp == SPP and world == 1) else None
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -372,7 +378,7 @@ def main():
             "gpu_launches": args.steps * 2,
             "kernel": {"name": "rrtb::k_render_pool<false>", "avg_ms": kern_s * 1e3, "share_of_step": kern_s / sec_per_step},
             "roofline": {"bound": "fp32_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T lane-instr/s",
-                         "frac": achieved / peak, "traffic": None, "w_ray": wr,
+                         "frac": achieved / peak, "traffic": traffic, "w_ray": wr,
                          "peak_source": "measured on this device by rrtb_probe_issue_rate: FFMA-only loop %.2f T lane-instr/s (an FFMA+FMNMX "
                                         "slab-test mix reaches %.2f); nominal 148 SM x 128 lanes x 1.965 GHz = 37.2; MEASURED_PEAKS.json "
                                         "has no FP32 figure" % (probe["ffma"] / 1e12, probe["ffma_fmnmx_mix"] / 1e12),

@@ -42,7 +42,7 @@ struct RenderArgs {
     unsigned long long n_items; // n_local_tiles * n_chunks * 32
     unsigned long long *accum;  // 3*W*H fixed-point sums
     int th_fetch, th_shade, th_leaf; // pool-scheduler thresholds (lanes)
-    int step_iters;                  // node visits per scheduling round
+    int step_iters, th_node;         // max node visits per scheduling round / lanes needed to continue
     unsigned long long *queue;  // [0] queue head, [1] rays, [2] box tests, [3] sphere, [4] msphere, [5] triangle tests, [6] hits
 };
 
@@ -420,6 +420,8 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     a.th_leaf = 8;
     a.step_iters = 4;
     if (const char *e = getenv("RRTB_STEP_ITERS")) a.step_iters = atoi(e);
+    a.th_node = 8;
+    if (const char *e = getenv("RRTB_TH_NODE")) a.th_node = atoi(e);
     if (const char *e = getenv("RRTB_TH_FETCH")) a.th_fetch = atoi(e); // tuning aids
     if (const char *e = getenv("RRTB_TH_SHADE")) a.th_shade = atoi(e);
     if (const char *e = getenv("RRTB_TH_LEAF")) a.th_leaf = atoi(e);
@@ -429,7 +431,7 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     RRTB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     int blocks = 0;
     int launches = 0;
-    if (a.n_items > 0) {
+    if (a.n_items > 0 && a.max_depth > 0) { // max_depth 0: the bounce loop never runs (rrt.cu:47), the image is black
         const bool bvh = ctx->use_bvh != 0, cnt = p->count_rays != 0;
         int rc;
         if (bvh && p->scheduler != RRTB_SCHED_SIMPLE) {

@@ -1,23 +1,28 @@
 // rrtb_render_pool.cuh -- scheduler RRTB_SCHED_POOL: a per-warp on-chip wavefront (sm_100a).
 //
-// Why (ncu, profiles/r01_ncu_sched_simple.md): with one path per lane a warp runs at ~7 of 32 lanes --
-// every lane waits for the slowest traversal of the round (node visits per ray: mean 12, tail > 60) and
-// the shading code runs once per round whatever the number of lanes that need it.
+// Why (ncu, profiles/README.md): with one path per lane a warp runs at 7-12 of 32 lanes -- every lane
+// waits for the slowest traversal of the round (node visits per ray: mean 12, tail > 60) and the shading
+// code runs once per round whatever the number of lanes that need it.
 //
-// Here each WARP owns a pool of POOL path slots in shared memory (60 B per slot, 228 KB/SM makes room for
-// 2048 slots per SM) and runs a small warp-synchronous scheduler over them:
+// Here each WARP owns a pool of POOL path slots in shared memory (60 B per slot; 228 KB/SM makes room for
+// 24 warps x 128 slots) and runs a small warp-synchronous scheduler over three stacks of slot ids:
 //
-//   FETCH  idle lanes pop a slot from the warp's trace stack, load its ray, start a traversal
-//   STEP   traversing lanes do ONE step: a BVH node visit, or (by warp vote) one exact leaf test;
-//          a lane whose traversal ends writes (t, leaf ref) to its slot, pushes it on the shade stack
-//          and becomes idle -- it does NOT wait for the other lanes
-//   SHADE  32 slots off the shade stack are shaded by 32 lanes (hit record, scatter / sky, accumulate);
-//          a finished path is replaced in place by the next camera path of the global work queue
-//          (one warp-aggregated atomicAdd per batch); slots with a new ray go back on the trace stack.
-//          Lanes that are in the middle of a traversal keep their traversal registers and resume.
+//   trace stack    slots whose ray awaits traversal
+//   scatter stack  slots whose segment HIT something  (hit record + material scatter next)
+//   gen stack      slots whose path ENDED (sky, absorbed, depth) or that never held one
 //
-// So traversal lanes are refilled as soon as they finish and shading always runs 32 wide; nothing but
-// the per-sample radiance (three 64-bit integer atomics into the L2-resident accumulator) leaves the SM.
+//   FETCH    idle lanes pop the trace stack, load the ray and start a traversal
+//   STEP     lanes in flight visit BVH nodes (the inner loop runs on while a vote finds enough of them),
+//            then, by vote, do one exact leaf test; a lane whose traversal ends writes (t, leaf ref) to its
+//            slot, pushes it on the scatter or the gen stack and is idle at once -- nobody waits for it
+//   SCATTER  32 hit slots, one per lane: hit record, Philox block, scatter; survivors -> trace stack
+//   GEN      32 ended slots, one per lane: sky x throughput into the accumulator (64-bit integer atomics),
+//            then the next camera paths of the global queue (ONE warp-aggregated atomicAdd per batch),
+//            Philox block, thin-lens ray -> trace stack
+//
+// SCATTER and GEN are separate batches so that each runs its own straight-line code 32 lanes wide (as one
+// batch the hit/miss branches serialised at ~15 lanes).  Lanes in the middle of a traversal keep their
+// traversal registers across a batch and resume.  Nothing but the per-path radiance leaves the SM.
 // Everything is keyed by (pixel, sample, bounce), so the image is bit-identical to the other schedulers.
 #pragma once
 
@@ -25,8 +30,7 @@ namespace rrtb {
 
 static constexpr int POOL = 128;               // path slots per warp
 static constexpr int POOL_WARPS = RENDER_TPB / 32;
-static constexpr int SLOT_FRESH = -2;          // hit_ref marker: slot holds no path yet / path ended
-static constexpr int STEP_ITERS = 4;           // node visits per scheduling round
+static constexpr int SLOT_FRESH = -2;          // hit_ref marker: nothing to accumulate for this slot
 
 struct WarpPool { // SoA, one per warp, in dynamic shared memory
     float ox[POOL], oy[POOL], oz[POOL], dx[POOL], dy[POOL], dz[POOL], tm[POOL];
@@ -34,8 +38,9 @@ struct WarpPool { // SoA, one per warp, in dynamic shared memory
     int pixel[POOL], sample[POOL], bounce[POOL];
     float hit_t[POOL];
     int hit_ref[POOL];
-    unsigned char tq[POOL]; // trace stack (slots whose ray awaits traversal)
-    unsigned char sq[POOL]; // shade stack (slots whose segment is traced, or fresh)
+    unsigned char tq[POOL]; // trace stack
+    unsigned char sq[POOL]; // scatter stack
+    unsigned char gq[POOL]; // gen stack
 };
 
 template <bool COUNT_RAYS>
@@ -50,14 +55,14 @@ __global__ void __launch_bounds__(RENDER_TPB, 3) k_render_pool(const RenderArgs 
     const float4 *__restrict__ leaves = s.leaves;
     const int2 *__restrict__ info = s.leaf_info;
 
-    // every slot starts fresh on the shade stack
+    // every slot starts on the gen stack with nothing to accumulate
     for (int k = lane; k < POOL; k += 32) {
-        wp.sq[k] = (unsigned char)k;
+        wp.gq[k] = (unsigned char)k;
         wp.hit_ref[k] = SLOT_FRESH;
     }
     __syncwarp();
     // stack heights are warp-uniform and live in registers: every lane derives them from the same ballots
-    int tq_n = 0, sq_n = POOL;
+    int tq_n = 0, sq_n = 0, gq_n = POOL;
 
     // lane state: the traversal in flight (slot < 0: idle, and then cur == TRAV_DONE)
     int slot = -1;
@@ -76,6 +81,8 @@ __global__ void __launch_bounds__(RENDER_TPB, 3) k_render_pool(const RenderArgs 
     while (true) {
         const unsigned idle_mask = __ballot_sync(0xffffffffu, slot < 0);
         const int n_idle = __popc(idle_mask);
+        // partial batches only when the trace stack is dry and enough lanes have nothing to do
+        const bool starving = tq_n == 0 && n_idle >= a.th_shade;
 
         if (n_idle >= a.th_fetch && tq_n > 0) {
             // ---------------- FETCH: idle lanes pop slots off the trace stack
@@ -94,159 +101,145 @@ __global__ void __launch_bounds__(RENDER_TPB, 3) k_render_pool(const RenderArgs 
             }
             tq_n -= take;
         }
-        else if (sq_n >= 32 || (sq_n > 0 && tq_n == 0 && n_idle >= a.th_shade)) {
-            // ---------------- SHADE: one batch of up to 32 slots, one per lane
+        else if (sq_n >= 32 || (starving && sq_n > 0 && sq_n >= gq_n)) {
+            // ---------------- SCATTER: up to 32 hit slots, one per lane (rrt.cu:50-60)
             const int take = min(32, sq_n);
             const bool mine = (int)lane < take;
-            int sl = mine ? wp.sq[sq_n - 1 - lane] : -1;
+            const int sl = mine ? wp.sq[sq_n - 1 - lane] : 0;
             sq_n -= take;
             __syncwarp(); // every lane has read its slot id before the stacks are pushed to below
-            bool want_new = false;   // path ended (or slot fresh): needs the next camera path
-            bool to_trace = false;   // slot has a ray to trace
-            int pixel = 0, sample = 0;
+            bool to_trace = false, ended = false;
             if (mine) {
-                const int href = wp.hit_ref[sl];
-                if (href == SLOT_FRESH) {
-                    want_new = true;
+                Ray r;
+                r.ox = wp.ox[sl]; r.oy = wp.oy[sl]; r.oz = wp.oz[sl];
+                r.dx = wp.dx[sl]; r.dy = wp.dy[sl]; r.dz = wp.dz[sl];
+                r.tm = wp.tm[sl];
+                const int bounce = wp.bounce[sl];
+                Hit h;
+                h.t = wp.hit_t[sl];
+                h.ref = wp.hit_ref[sl];
+                h.obj = -1;
+                if (COUNT_RAYS) {
+                    ++rays;
+                    ++hits;
                 }
-                else {
-                    Ray r;
-                    r.ox = wp.ox[sl]; r.oy = wp.oy[sl]; r.oz = wp.oz[sl];
-                    r.dx = wp.dx[sl]; r.dy = wp.dy[sl]; r.dz = wp.dz[sl];
-                    r.tm = wp.tm[sl];
-                    float thr_r = wp.tr[sl], thr_g = wp.tg[sl], thr_b = wp.tb[sl];
-                    pixel = wp.pixel[sl];
-                    sample = wp.sample[sl];
-                    int bounce = wp.bounce[sl];
-                    if (COUNT_RAYS) {
-                        ++rays;
-                        if (href >= 0) ++hits;
-                    }
-                    float lr = 0.f, lg = 0.f, lb = 0.f;
-                    bool path_end = false;
-                    if (href < 0) { // sky (rrt.cu:68-75)
-                        float cr, cg, cb;
-                        sky(r, cr, cg, cb);
-                        lr = thr_r * cr;
-                        lg = thr_g * cg;
-                        lb = thr_b * cb;
-                        path_end = true;
-                    }
-                    else {
-                        Hit h;
-                        h.t = wp.hit_t[sl];
-                        h.ref = href;
-                        h.obj = -1;
-                        HitRecord rec = hit_record(leaves, info, r, h);
-                        uint4 rnd = philox4x32_10(make_uint4((uint32_t)pixel, (uint32_t)sample, 2u + (uint32_t)bounce, 0u), a.key);
-                        float4 m = __ldg(&s.materials[rec.mat]);
-                        int mtype = __ldg(&s.material_type[rec.mat]);
-                        float dx, dy, dz, ar, ag, ab;
-                        if (scatter(mtype, m, r, rec, rnd, dx, dy, dz, ar, ag, ab)) {
-                            if (++bounce >= a.max_depth) {
-                                path_end = true; // exceeded depth: black (rrt.cu:78)
-                            }
-                            else {
-                                wp.ox[sl] = rec.px; wp.oy[sl] = rec.py; wp.oz[sl] = rec.pz;
-                                wp.dx[sl] = dx; wp.dy[sl] = dy; wp.dz[sl] = dz;
-                                wp.tr[sl] = thr_r * ar; wp.tg[sl] = thr_g * ag; wp.tb[sl] = thr_b * ab;
-                                wp.bounce[sl] = bounce;
-                                to_trace = true;
-                            }
-                        }
-                        else {
-                            path_end = true; // absorbed: black (rrt.cu:61-63)
-                        }
-                    }
-                    if (path_end) {
-                        unsigned long long *dst = a.accum + 3ull * (unsigned long long)pixel;
-                        const unsigned long long fr = to_fixed(lr), fg = to_fixed(lg), fb = to_fixed(lb);
-                        if (fr) atomicAdd(dst + 0, fr);
-                        if (fg) atomicAdd(dst + 1, fg);
-                        if (fb) atomicAdd(dst + 2, fb);
-                        want_new = true;
-                    }
+                HitRecord rec = hit_record(leaves, info, r, h);
+                uint4 rnd = philox4x32_10(make_uint4((uint32_t)wp.pixel[sl], (uint32_t)wp.sample[sl], 2u + (uint32_t)bounce, 0u), a.key);
+                float4 m = __ldg(&s.materials[rec.mat]);
+                int mtype = __ldg(&s.material_type[rec.mat]);
+                float dx, dy, dz, ar, ag, ab;
+                if (scatter(mtype, m, r, rec, rnd, dx, dy, dz, ar, ag, ab) && bounce + 1 < a.max_depth) {
+                    wp.ox[sl] = rec.px; wp.oy[sl] = rec.py; wp.oz[sl] = rec.pz;
+                    wp.dx[sl] = dx; wp.dy[sl] = dy; wp.dz[sl] = dz;
+                    wp.tr[sl] *= ar; wp.tg[sl] *= ag; wp.tb[sl] *= ab;
+                    wp.bounce[sl] = bounce + 1;
+                    to_trace = true;
+                }
+                else { // absorbed (rrt.cu:61-63) or depth exhausted (rrt.cu:78): black, nothing to accumulate
+                    wp.hit_ref[sl] = SLOT_FRESH;
+                    ended = true;
                 }
             }
-            // next camera paths for the slots that ended: one warp-aggregated atomic on the global queue
-            unsigned new_mask = __ballot_sync(0xffffffffu, want_new);
-            if (new_mask && !queue_empty) {
+            const unsigned t_mask = __ballot_sync(0xffffffffu, to_trace);
+            const unsigned e_mask = __ballot_sync(0xffffffffu, ended);
+            if (to_trace) wp.tq[tq_n + __popc(t_mask & lt_mask)] = (unsigned char)sl;
+            if (ended) wp.gq[gq_n + __popc(e_mask & lt_mask)] = (unsigned char)sl;
+            tq_n += __popc(t_mask);
+            gq_n += __popc(e_mask);
+            __syncwarp(); // slot contents + stack entries visible to the lanes that will pop them
+        }
+        else if (gq_n >= 32 || (starving && gq_n > 0)) {
+            // ---------------- GEN: up to 32 ended slots, one per lane: accumulate, then regenerate
+            const int take = min(32, gq_n);
+            const bool mine = (int)lane < take;
+            const int sl = mine ? wp.gq[gq_n - 1 - lane] : 0;
+            gq_n -= take;
+            __syncwarp();
+            if (mine && wp.hit_ref[sl] == -1) { // the segment left the scene: sky x throughput (rrt.cu:68-75)
+                if (COUNT_RAYS) ++rays;
+                Ray r;
+                r.dx = wp.dx[sl]; r.dy = wp.dy[sl]; r.dz = wp.dz[sl];
+                float cr, cg, cb;
+                sky(r, cr, cg, cb);
+                unsigned long long *dst = a.accum + 3ull * (unsigned long long)wp.pixel[sl];
+                atomicAdd(dst + 0, to_fixed(wp.tr[sl] * cr));
+                atomicAdd(dst + 1, to_fixed(wp.tg[sl] * cg));
+                atomicAdd(dst + 2, to_fixed(wp.tb[sl] * cb));
+            }
+            // next camera paths: one warp-aggregated atomic on the global queue
+            bool to_trace = false;
+            if (!queue_empty) {
                 unsigned long long base = 0;
-                const int leader = __ffs(new_mask) - 1;
-                if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(new_mask));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (base + (unsigned long long)__popc(new_mask) >= a.n_items) queue_empty = true;
-                // decode (local tile, local sample) of the first item once per warp (64-bit division), the
+                if (lane == 0) base = atomicAdd(a.queue, (unsigned long long)take);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + (unsigned long long)take >= a.n_items) queue_empty = true;
+                // decode (local tile, local sample) of the first item once per warp (64-bit division); the
                 // other lanes are at most one (tile, sample) group further on
                 const unsigned long long ts0 = base >> 5;
                 int ls0 = 0, ltile0 = 0;
-                if ((int)lane == leader) {
+                if (lane == 0) {
                     ltile0 = (int)(ts0 / (unsigned long long)a.n_local_samples);
                     ls0 = (int)(ts0 - (unsigned long long)ltile0 * (unsigned long long)a.n_local_samples);
                 }
-                ls0 = __shfl_sync(0xffffffffu, ls0, leader);
-                ltile0 = __shfl_sync(0xffffffffu, ltile0, leader);
-                if (want_new) {
-                    const unsigned long long item = base + __popc(new_mask & lt_mask);
-                    if (item < a.n_items) {
-                        // item = (local_tile * n_local_samples + local_sample) * 32 + pixel_in_tile
-                        const unsigned pit = (unsigned)(item & 31ull);
-                        int ls = ls0 + (int)((item >> 5) - ts0), ltile = ltile0;
-                        if (ls >= a.n_local_samples) {
-                            ls -= a.n_local_samples;
-                            ++ltile;
-                        }
-                        const int tile = a.shard_mode == RRTB_SHARD_TILES ? ltile * a.world + a.rank : ltile;
-                        int ty = (int)__fdividef((float)tile, (float)a.tiles_x); // float estimate, off by <= 1 ...
-                        int tx = tile - ty * a.tiles_x;
-                        if (tx < 0) { // ... corrected exactly in integers
-                            --ty;
-                            tx += a.tiles_x;
-                        }
-                        else if (tx >= a.tiles_x) {
-                            ++ty;
-                            tx -= a.tiles_x;
-                        }
-                        const int i = tx * 8 + (int)(pit & 7u), j = ty * 4 + (int)(pit >> 3);
-                        if (i < a.W && j < a.H) { // else: padding pixel of an edge tile -> slot stays fresh
-                            pixel = j * a.W + i;
-                            sample = a.shard_mode == RRTB_SHARD_SAMPLES ? ls * a.world + a.rank : ls;
-                            Ray r = camera_ray(a.cam, a.W, a.H, i, j, sample, a.key);
-                            wp.ox[sl] = r.ox; wp.oy[sl] = r.oy; wp.oz[sl] = r.oz;
-                            wp.dx[sl] = r.dx; wp.dy[sl] = r.dy; wp.dz[sl] = r.dz;
-                            wp.tm[sl] = r.tm;
-                            wp.tr[sl] = 1.f; wp.tg[sl] = 1.f; wp.tb[sl] = 1.f;
-                            wp.pixel[sl] = pixel;
-                            wp.sample[sl] = sample;
-                            wp.bounce[sl] = 0;
-                            to_trace = true;
-                            want_new = false;
-                        }
+                ls0 = __shfl_sync(0xffffffffu, ls0, 0);
+                ltile0 = __shfl_sync(0xffffffffu, ltile0, 0);
+                const unsigned long long item = base + lane;
+                if (mine && item < a.n_items) {
+                    // item = (local_tile * n_local_samples + local_sample) * 32 + pixel_in_tile
+                    const unsigned pit = (unsigned)(item & 31ull);
+                    int ls = ls0 + (int)((item >> 5) - ts0), ltile = ltile0;
+                    if (ls >= a.n_local_samples) {
+                        ls -= a.n_local_samples;
+                        ++ltile;
+                    }
+                    const int tile = a.shard_mode == RRTB_SHARD_TILES ? ltile * a.world + a.rank : ltile;
+                    int ty = (int)__fdividef((float)tile, (float)a.tiles_x); // float estimate, off by <= 1 ...
+                    int tx = tile - ty * a.tiles_x;
+                    if (tx < 0) { // ... corrected exactly in integers
+                        --ty;
+                        tx += a.tiles_x;
+                    }
+                    else if (tx >= a.tiles_x) {
+                        ++ty;
+                        tx -= a.tiles_x;
+                    }
+                    const int i = tx * 8 + (int)(pit & 7u), j = ty * 4 + (int)(pit >> 3);
+                    if (i < a.W && j < a.H) { // else: padding pixel of an edge tile, the slot asks again
+                        const int sample = a.shard_mode == RRTB_SHARD_SAMPLES ? ls * a.world + a.rank : ls;
+                        Ray r = camera_ray(a.cam, a.W, a.H, i, j, sample, a.key); // rrt.cu:112-114, camera.h:31-38
+                        wp.ox[sl] = r.ox; wp.oy[sl] = r.oy; wp.oz[sl] = r.oz;
+                        wp.dx[sl] = r.dx; wp.dy[sl] = r.dy; wp.dz[sl] = r.dz;
+                        wp.tm[sl] = r.tm;
+                        wp.tr[sl] = 1.f; wp.tg[sl] = 1.f; wp.tb[sl] = 1.f;
+                        wp.pixel[sl] = j * a.W + i;
+                        wp.sample[sl] = sample;
+                        wp.bounce[sl] = 0;
+                        to_trace = true;
                     }
                 }
             }
-            // route the slots: traced next / fresh again (retry while the queue has work) / dead
-            const bool refresh = want_new && !queue_empty; // padding pixel: ask again
-            const bool die = want_new && queue_empty;
-            if (want_new) wp.hit_ref[sl] = SLOT_FRESH;
+            // route: new ray -> trace stack; padding pixel -> gen stack again while the queue has work; else dead
+            const bool again = mine && !to_trace && !queue_empty;
+            if (mine && !to_trace) wp.hit_ref[sl] = SLOT_FRESH;
             const unsigned t_mask = __ballot_sync(0xffffffffu, to_trace);
-            const unsigned f_mask = __ballot_sync(0xffffffffu, refresh);
-            const unsigned d_mask = __ballot_sync(0xffffffffu, die);
-            (void)d_mask;
+            const unsigned g_mask = __ballot_sync(0xffffffffu, again);
             if (to_trace) wp.tq[tq_n + __popc(t_mask & lt_mask)] = (unsigned char)sl;
-            if (refresh) wp.sq[sq_n + __popc(f_mask & lt_mask)] = (unsigned char)sl;
+            if (again) wp.gq[gq_n + __popc(g_mask & lt_mask)] = (unsigned char)sl;
             tq_n += __popc(t_mask);
-            sq_n += __popc(f_mask);
-            __syncwarp(); // slot contents + stack entries visible to the lanes that will pop them
+            gq_n += __popc(g_mask);
+            __syncwarp();
         }
         else if (n_idle == 32) {
-            break; // nothing in flight, nothing to fetch (tq_n == 0), nothing to shade (sq_n == 0): all slots are dead
+            break; // nothing in flight and all three stacks empty: every slot is dead
         }
         else {
-            // ---------------- STEP: a few node visits, then (by vote) one exact leaf test
+            // ---------------- STEP: node visits continue while at least th_node lanes still have a node to
+            // visit (one vote per visit, at most step_iters in a row), then, by vote, one exact leaf test
+            int it = 0;
 #pragma unroll 1
-            for (int it = 0; it < a.step_iters; ++it)
+            do {
                 if (cur >= 0) node_step<COUNT_RAYS>(nodes, pre, 0.001f, best.t, cur, sp, stack, tc);
+            } while (++it < a.step_iters && __popc(__ballot_sync(0xffffffffu, cur >= 0)) >= a.th_node);
             const bool at_leaf = cur < 0 && cur != TRAV_DONE;
             const unsigned leaf_mask = __ballot_sync(0xffffffffu, at_leaf);
             if (leaf_mask) {
@@ -259,13 +252,18 @@ __global__ void __launch_bounds__(RENDER_TPB, 3) k_render_pool(const RenderArgs 
             const bool fin = slot >= 0 && cur == TRAV_DONE;
             const unsigned fin_mask = __ballot_sync(0xffffffffu, fin);
             if (fin_mask) {
+                const bool hit = fin && best.ref >= 0;
+                const unsigned hit_mask = __ballot_sync(0xffffffffu, hit);
+                const unsigned miss_mask = fin_mask & ~hit_mask;
                 if (fin) {
                     wp.hit_t[slot] = best.t;
                     wp.hit_ref[slot] = best.ref; // -1 = miss
-                    wp.sq[sq_n + __popc(fin_mask & lt_mask)] = (unsigned char)slot;
+                    if (hit) wp.sq[sq_n + __popc(hit_mask & lt_mask)] = (unsigned char)slot;
+                    else wp.gq[gq_n + __popc(miss_mask & lt_mask)] = (unsigned char)slot;
                     slot = -1;
                 }
-                sq_n += __popc(fin_mask);
+                sq_n += __popc(hit_mask);
+                gq_n += __popc(miss_mask);
                 __syncwarp();
             }
         }
