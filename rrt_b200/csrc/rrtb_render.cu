@@ -418,9 +418,9 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     a.th_fetch = 16;
     a.th_shade = 32;
     a.th_leaf = 8;
-    a.step_iters = 4;
+    a.step_iters = 8;
     if (const char *e = getenv("RRTB_STEP_ITERS")) a.step_iters = atoi(e);
-    a.th_node = 8;
+    a.th_node = 12;
     if (const char *e = getenv("RRTB_TH_NODE")) a.th_node = atoi(e);
     if (const char *e = getenv("RRTB_TH_FETCH")) a.th_fetch = atoi(e); // tuning aids
     if (const char *e = getenv("RRTB_TH_SHADE")) a.th_shade = atoi(e);
