@@ -34,6 +34,43 @@ METRIC = "Mrays/s on scenes/final.txt 1200x800 (500 spp, depth 50)"
 UNIT = "Mrays/s"
 
 
+WORKLOADS = {  # BASELINE.json configs[1..4]; configs[0] is the reference's own CPU case (a parity-test size)
+    "final": dict(W=1200, H=800, spp=500, label="scenes/final.txt", config="BASELINE.json configs[1]", data="reference scene file scenes/final.txt"),
+    "test3": dict(W=1920, H=1080, spp=256, label="scenes/test3.txt (motion blur)", config="BASELINE.json configs[2]", data="reference scene file scenes/test3.txt"),
+    "test2": dict(W=1920, H=1080, spp=256, label="scenes/test2.txt (triangles)", config="BASELINE.json configs[3]", data="reference scene file scenes/test2.txt"),
+    "synthetic": dict(W=3840, H=2160, spp=1024, label="synthetic 1 003 520 triangles + 100 004 spheres", config="BASELINE.json configs[4]",
+                      data="synthetic scene generated in the reference grammar (rrt_b200/synthetic.py, seed 20221005)"),
+    "synthetic_small": dict(W=3840, H=2160, spp=64, label="synthetic 250 880 triangles + 20 004 spheres", config="scaled-down sibling of configs[4]",
+                            data="synthetic scene generated in the reference grammar (rrt_b200/synthetic.py, seed 20221005)"),
+}
+
+
+def load_workload(name, Wl, Hl):
+    import tempfile
+
+    import numpy as np
+
+    from rrt_b200 import Scene, SceneArrays
+
+    if name == "final" and (Wl, Hl) == (W, H):
+        return final_scene()
+    if name in ("final", "test2", "test3"):
+        for base in (os.path.join(ROOT, "oracle", "_ref", "scenes"), "/root/reference/scenes"):
+            p = os.path.join(base, name + ".txt")
+            if os.path.exists(p):
+                return Scene.from_file(p, Wl, Hl).arrays, p
+        d = np.load(os.path.join(ROOT, "tests", "golden", "scene_%s.npz" % name))  # camera derived for the config's aspect
+        return SceneArrays.from_npz_dict(d), "tests/golden/scene_%s.npz" % name
+    from rrt_b200.synthetic import write_synthetic_scene
+
+    kw = dict(n_spheres=100_000, ico_level=5, grid=7) if name == "synthetic" else dict(n_spheres=20_000, ico_level=4, grid=7)
+    p = os.path.join(tempfile.gettempdir(), "rrtb_%s_%d.txt" % (name, os.getpid()))
+    write_synthetic_scene(p, **kw)
+    arrays = Scene.from_file(p, Wl, Hl).arrays
+    os.remove(p)
+    return arrays, "generated"
+
+
 def final_scene():
     """scenes/final.txt.  Parsed by the product's own parser when the text is staged (oracle/_ref/scenes,
     which travels to the GPU box); otherwise the committed golden arrays, which are bit-identical to the
@@ -233,6 +270,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="debug only: any value other than 500 is not the headline config")
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu / reference-GPU baselines (profiling runs)")
+    ap.add_argument("--workload", default="final", choices=sorted(WORKLOADS), help="final = the headline (BASELINE.json configs[1]); the others are the remaining configs")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--shard", default="tiles", choices=["tiles", "samples"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -255,16 +296,20 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    spp = args.spp
+    wl = WORKLOADS[args.workload]
+    Wl, Hl = args.width or wl["W"], args.height or wl["H"]
+    spp = args.spp if (args.spp != SPP or args.workload == "final") else wl["spp"]
+    headline = args.workload == "final" and spp == SPP and (Wl, Hl) == (W, H)
+    shard_mode = 0 if args.shard == "tiles" else 1
 
-    scene, scene_src = final_scene()
+    scene, scene_src = load_workload(args.workload, Wl, Hl)
     ctx = Context(local_rank)
     ctx.set_scene(scene, use_bvh=True)
-    n = 3 * W * H
+    n = 3 * Wl * Hl
     acc = torch.zeros(n, dtype=torch.int64, device=dev)
     out = torch.empty(n, dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-    params = ctx.params(W, H, spp, DEPTH, SEED, rank, world, 0, False)
+    params = ctx.params(Wl, Hl, spp, DEPTH, SEED, rank, world, shard_mode, False)
 
     def barrier():
         if world > 1:
@@ -286,7 +331,7 @@ def main():
             ctx.resolve_device(acc.data_ptr(), out.data_ptr(), n)
 
     # counting pass (untimed): rays and per-ray work of exactly this workload and shard
-    pc = ctx.params(W, H, spp, DEPTH, SEED, rank, world, 0, True)
+    pc = ctx.params(Wl, Hl, spp, DEPTH, SEED, rank, world, shard_mode, True)
     acc.zero_()
     torch.cuda.synchronize()
     cst = ctx.render_device(pc, acc.data_ptr())
@@ -323,14 +368,14 @@ def main():
     value = total_rays / sec_per_step / 1e6
 
     # ---- e2e: through the C ABI with host buffers, every step: scene upload + LBVH build + render + D2H
-    host_out = np.empty((H, W, 3), np.float32)
+    host_out = np.empty((Hl, Wl, 3), np.float32)
     h2d = scene.camera.nbytes + scene.materials.nbytes + scene.spheres.nbytes + scene.mspheres.nbytes + scene.triangles.nbytes
     d2h = host_out.nbytes if rank == 0 else 0
 
     def e2e_step():
         ctx.set_scene(scene, use_bvh=True)
         if world == 1:
-            ctx.render(W, H, spp, DEPTH, SEED, out=host_out)
+            ctx.render(Wl, Hl, spp, DEPTH, SEED, out=host_out)
         else:
             acc.zero_()
             torch.cuda.synchronize()
@@ -362,15 +407,15 @@ def main():
         traffic = None  # dram bytes per launch of the render kernel, from the committed ncu --set full capture
         try:
             with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
-                traffic = json.load(f)["traffic_bytes_per_launch"] if (spp == SPP and world == 1) else None
+                traffic = json.load(f)["traffic_bytes_per_launch"] if (headline and world == 1) else None
         except Exception:
             pass
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if args.workload == "final" else "Mrays/s on %s" % wl["label"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 (f64 leaf discriminants, u64 fixed-point accumulation)", "data": "synthetic-free: reference scene file scenes/final.txt (%s)" % scene_src,
-            "config": {"workload": "scenes/final.txt 1200x800, %d spp, depth 50 (BASELINE.json configs[1])" % spp, "prims": scene.n_objects,
-                       "sharding": "one image, interleaved 8x4 tiles over %d GPU(s), NCCL reduce of u64 accumulators" % world,
+            "dtype": "f32 (f64 leaf discriminants, u64 fixed-point accumulation)", "data": "%s (%s)" % (wl["data"], scene_src),
+            "config": {"workload": "%s %dx%d, %d spp, depth 50 (%s)" % (wl["label"], Wl, Hl, spp, wl["config"]), "prims": scene.n_objects,
+                       "sharding": "one image, %s over %d GPU(s), NCCL reduce of u64 accumulators" % ("interleaved 8x4 tiles" if shard_mode == 0 else "interleaved samples", world),
                        "l2": "256 MiB flush written between timed iterations", "rays_per_step": total_rays,
                        "rays_per_path": total_rays / tot["paths"], **{k: round(x, 4) for k, x in v.items()}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -382,11 +427,11 @@ def main():
                          "peak_source": "measured on this device by rrtb_probe_issue_rate: FFMA-only loop %.2f T lane-instr/s (an FFMA+FMNMX "
                                         "slab-test mix reaches %.2f); nominal 148 SM x 128 lanes x 1.965 GHz = 37.2; MEASURED_PEAKS.json "
                                         "has no FP32 figure" % (probe["ffma"] / 1e12, probe["ffma_fmnmx_mix"] / 1e12),
-                         "hbm_note": "scene + LBVH = %d KB, L1/L2 resident: HBM traffic is the 23 MB accumulator only" % ((scene.n_objects * (64 + 48 + 8)) // 1024)},
+                         "hbm_note": "scene + LBVH = %d KB (L1/L2 resident); HBM traffic is the %d MB u64 accumulator" % ((scene.n_objects * (64 + 48 + 8)) // 1024, n * 8 // 2**20)},
             "clocks": clocks,
             "wall_s": wall,
         }
-        if world == 1 and not args.no_baselines:
+        if world == 1 and not args.no_baselines and args.workload == "final":
             line["cpu_baseline"] = cpu_baseline_sample(total_rays / tot["paths"])
             g = reference_gpu_baseline()
             if g:
