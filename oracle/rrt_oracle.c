@@ -242,7 +242,9 @@ static int triangle_t(f3 o, f3 d, f3 v0, f3 e1f, f3 e2f, float t_min, float t_ma
     }
     double tn = fma(e2z, qz, fma(e2y, qy, e2x * qx));
     float t = (float)tn / (float)det;
-    if (t > 1e-7f && t > t_min && t < t_max) { /* exclusive, triangle.h:61 */
+    /* triangle.h:61 is exclusive at both ends; t == t_max (an exact tie with the current closest hit) is let
+     * through here and settled by candidate_wins, which restates that exclusivity order-independently */
+    if (t > 1e-7f && t > t_min && t <= t_max) {
         *t_out = t;
         return 1;
     }
@@ -562,7 +564,10 @@ static int closest_bvh(const orc_scene *s, const orc_bvh *b, f3 o, f3 d, float t
         *t_out = best;
         return bid;
     }
-    f3 inv = F3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    /* direction components of (almost) exactly zero would make the FMA-form slab test compute inf - inf */
+    f3 ds = F3(fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x, fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y,
+               fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z);
+    f3 inv = F3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
     f3 ood = F3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
     int32_t stack[128];
     int sp = 0;

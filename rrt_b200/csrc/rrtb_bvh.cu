@@ -380,6 +380,14 @@ __global__ void __launch_bounds__(TPB) k_refit(const uint64_t *__restrict__ keys
     }
 }
 
+// traversal boxes are stored as centre + half extent (see box_hit): c +- h encloses [lo, hi] padded by `pad`
+// (the roundings of c and of hi-c / c-lo are <= 2^-23 * magnitude, pad is 2^-20 * magnitude)
+__device__ __forceinline__ void center_half(float lo, float hi, float pad, float &c, float &h)
+{
+    c = 0.5f * (lo + hi);
+    h = fmaxf(hi - c, c - lo) + pad;
+}
+
 __device__ __forceinline__ int prim_type(int id, int ns, int nms) { return id < ns ? PRIM_SPHERE : (id < ns + nms ? PRIM_MSPHERE : PRIM_TRIANGLE); }
 
 __global__ void __launch_bounds__(TPB) k_flatten_nodes(const uint64_t *__restrict__ keys, int n, int ns, int nms,
@@ -394,12 +402,12 @@ __global__ void __launch_bounds__(TPB) k_flatten_nodes(const uint64_t *__restric
     if (n == 1) { // degenerate tree: both children of the root are the only leaf (as bvh.h:116-118 does)
         if (i == 0) {
             const float *b = prim_box;
-            float lo0 = __fsub_rn(b[0], pad), lo1 = __fsub_rn(b[1], pad), lo2 = __fsub_rn(b[2], pad);
-            float hi0 = __fadd_rn(b[3], pad), hi1 = __fadd_rn(b[4], pad), hi2 = __fadd_rn(b[5], pad);
+            float c[3], h[3];
+            for (int k = 0; k < 3; ++k) center_half(b[k], b[3 + k], pad, c[k], h[k]);
             int enc = ~((0 << 2) | prim_type(0, ns, nms));
-            nodes[0] = make_float4(lo0, lo1, lo2, hi0);
-            nodes[1] = make_float4(hi1, hi2, lo0, lo1);
-            nodes[2] = make_float4(lo2, hi0, hi1, hi2);
+            nodes[0] = make_float4(c[0], c[1], c[2], h[0]);
+            nodes[1] = make_float4(h[1], h[2], c[0], c[1]);
+            nodes[2] = make_float4(c[2], h[0], h[1], h[2]);
             nodes[3] = make_float4(__int_as_float(enc), __int_as_float(enc), 0.f, 0.f);
         }
         return;
@@ -420,10 +428,7 @@ __global__ void __launch_bounds__(TPB) k_flatten_nodes(const uint64_t *__restric
             b = prim_box + 6 * id;
             enc[c] = ~((slot << 2) | prim_type(id, ns, nms));
         }
-        for (int k = 0; k < 3; ++k) {
-            bx[c][k] = __fsub_rn(b[k], pad);
-            bx[c][3 + k] = __fadd_rn(b[3 + k], pad);
-        }
+        for (int k = 0; k < 3; ++k) center_half(b[k], b[3 + k], pad, bx[c][k], bx[c][3 + k]);
     }
     nodes[4 * i + 0] = make_float4(bx[0][0], bx[0][1], bx[0][2], bx[0][3]);
     nodes[4 * i + 1] = make_float4(bx[0][4], bx[0][5], bx[1][0], bx[1][1]);

@@ -29,7 +29,7 @@ namespace rrtb {
 //   triangle       a = (v0.xyz, n.x) b = (e1.xyz, n.y)      c = (e2.xyz, n.z)    n = unit face normal
 // leaf_info[k] = (object id, material index)
 // BVH node: 4 x float4 (64 B): padded boxes of both children + child refs
-//   n0 = (L.min.xyz, L.max.x)  n1 = (L.max.y, L.max.z, R.min.x, R.min.y)  n2 = (R.min.z, R.max.xyz)
+//   n0 = (L.c.xyz, L.h.x)  n1 = (L.h.y, L.h.z, R.c.x, R.c.y)  n2 = (R.c.z, R.h.xyz)   c = centre, h = half extent
 //   n3 = (bits(left ref), bits(right ref), -, -)
 // child ref >= 0: internal node index;  < 0: leaf, ~ref = (leaf slot << 2) | type
 enum : int { PRIM_SPHERE = 0, PRIM_MSPHERE = 1, PRIM_TRIANGLE = 2 };
@@ -154,9 +154,10 @@ __device__ __forceinline__ float rcp_approx(float x)
 __device__ __forceinline__ RayPre ray_pre(const Ray &r)
 {
     RayPre p;
-    p.ix = rcp_approx(r.dx);
-    p.iy = rcp_approx(r.dy);
-    p.iz = rcp_approx(r.dz);
+    // a direction component of (almost) exactly zero would make the FMA-form slab test compute inf - inf
+    p.ix = rcp_approx(fabsf(r.dx) < 1e-20f ? copysignf(1e-20f, r.dx) : r.dx);
+    p.iy = rcp_approx(fabsf(r.dy) < 1e-20f ? copysignf(1e-20f, r.dy) : r.dy);
+    p.iz = rcp_approx(fabsf(r.dz) < 1e-20f ? copysignf(1e-20f, r.dz) : r.dz);
     p.oox = -r.ox * p.ix;
     p.ooy = -r.oy * p.iy;
     p.ooz = -r.oz * p.iz;
@@ -177,15 +178,18 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
     return r;
 }
 
-// slab test on one (already padded) box; inclusive; returns entry distance in tn
-__device__ __forceinline__ bool box_hit(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
-                                        const RayPre &p, float t_min, float t_max, float &tn)
+// Slab test on one (already padded) box given as centre c and half extent h; inclusive; entry distance in tn.
+// Per axis  t_c = (c - o)/d,  u = h/d  ->  [t_c - |u|, t_c + |u|]:  FFMA + FMUL + 2 FADD(|.|), no min/max to
+// order the two planes.  A box costs 12 fma-pipe ops + 2 FMNMX3 + 2 FMNMX + 1 FSETP on the alu pipe, instead
+// of 6 + 11: ncu showed the alu pipe (half the fma pipe's rate) as the busiest unit of the render kernel.
+__device__ __forceinline__ bool box_hit(float cx, float cy, float cz, float hx, float hy, float hz, const RayPre &p,
+                                        float t_min, float t_max, float &tn)
 {
-    float x0 = __fmaf_rn(bminx, p.ix, p.oox), x1 = __fmaf_rn(bmaxx, p.ix, p.oox);
-    float y0 = __fmaf_rn(bminy, p.iy, p.ooy), y1 = __fmaf_rn(bmaxy, p.iy, p.ooy);
-    float z0 = __fmaf_rn(bminz, p.iz, p.ooz), z1 = __fmaf_rn(bmaxz, p.iz, p.ooz);
-    tn = fmaxf(fmax3(fminf(x0, x1), fminf(y0, y1), fminf(z0, z1)), t_min);
-    float tf = fminf(fmin3(fmaxf(x0, x1), fmaxf(y0, y1), fmaxf(z0, z1)), t_max);
+    float tx = fmaf(cx, p.ix, p.oox), ux = fabsf(hx * p.ix);
+    float ty = fmaf(cy, p.iy, p.ooy), uy = fabsf(hy * p.iy);
+    float tz = fmaf(cz, p.iz, p.ooz), uz = fabsf(hz * p.iz);
+    tn = fmaxf(fmax3(tx - ux, ty - uy, tz - uz), t_min);
+    float tf = fminf(fmin3(tx + ux, ty + uy, tz + uz), t_max);
     return tn <= tf;
 }
 
@@ -256,7 +260,9 @@ __device__ __forceinline__ bool triangle_test(const Ray &r, float4 A, float4 B, 
     }
     double tn = __fma_rn(e2z, qz, __fma_rn(e2y, qy, __dmul_rn(e2x, qx)));
     float t = __fdiv_rn(__double2float_rn(tn), __double2float_rn(det));
-    if (t > 1e-7f && t > t_min && t < t_max) {
+    // triangle.h:61 is exclusive at both ends; an exact tie with the current closest hit (t == t_max) is let
+    // through and settled by candidate_wins, which restates that exclusivity order-independently
+    if (t > 1e-7f && t > t_min && t <= t_max) {
         t_out = t;
         return true;
     }

@@ -435,7 +435,7 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
         const bool bvh = ctx->use_bvh != 0, cnt = p->count_rays != 0;
         int rc;
         if (bvh && p->scheduler != RRTB_SCHED_SIMPLE) {
-            rc = cnt ? launch_pool(ctx, k_render_pool<true>, a, &blocks) : launch_pool(ctx, k_render_pool<false>, a, &blocks);
+            rc = cnt ? launch_pool(ctx, k_render_pool<true, 2>, a, &blocks) : launch_pool(ctx, k_render_pool<false, 2>, a, &blocks);
         }
         else if (bvh && cnt) rc = launch_render_t<true, true>(ctx, a, &blocks);
         else if (bvh) rc = launch_render_t<true, false>(ctx, a, &blocks);

@@ -30,7 +30,6 @@ namespace rrtb {
 
 static constexpr int POOL = 96;                // path slots per warp
 static constexpr int POOL_WARPS = RENDER_TPB / 32;
-static constexpr int NODE_UNROLL = 2;          // node visits between two continue-votes
 static constexpr int SLOT_FRESH = -2;          // hit_ref marker: nothing to accumulate for this slot
 
 struct WarpPool { // SoA, one per warp, in dynamic shared memory
@@ -44,7 +43,7 @@ struct WarpPool { // SoA, one per warp, in dynamic shared memory
     unsigned char gq[POOL]; // gen stack
 };
 
-template <bool COUNT_RAYS>
+template <bool COUNT_RAYS, int NODE_UNROLL>
 __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -239,8 +238,9 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
             int it = 0;
 #pragma unroll 1
             do {
-                if (cur >= 0) node_step<COUNT_RAYS>(nodes, pre, 0.001f, best.t, cur, sp, stack, tc);
-                if (NODE_UNROLL > 1 && cur >= 0) node_step<COUNT_RAYS>(nodes, pre, 0.001f, best.t, cur, sp, stack, tc);
+#pragma unroll
+                for (int u = 0; u < NODE_UNROLL; ++u) // node visits between two continue-votes
+                    if (cur >= 0) node_step<COUNT_RAYS>(nodes, pre, 0.001f, best.t, cur, sp, stack, tc);
             } while (++it < a.step_iters && __popc(__ballot_sync(0xffffffffu, cur >= 0)) >= a.th_node);
             const bool at_leaf = cur < 0 && cur != TRAV_DONE;
             const unsigned leaf_mask = __ballot_sync(0xffffffffu, at_leaf);

@@ -1,0 +1,164 @@
+"""GPU edge cases (-m gpu): degenerate scene sizes, ties, inside-sphere rays, depth limits, tiny images,
+camera-only updates, and the error paths of the C ABI."""
+import numpy as np
+import pytest
+
+from oracle_lib import Oracle, camera_derive
+from rrt_b200.types import SceneArrays, material_dtype, msphere_dtype, sphere_dtype, triangle_dtype
+
+pytestmark = pytest.mark.gpu
+
+
+def make_scene(spheres=(), tris=(), mspheres=(), cam=None, shutter=(0.0, 0.0)):
+    mats = np.zeros(3, material_dtype)
+    mats["type"] = [0, 1, 2]
+    mats["albedo"][0] = (0.6, 0.5, 0.4)
+    mats["albedo"][1] = (0.8, 0.8, 0.9)
+    mats["param"] = [0, 0.2, 1.5]
+    s = np.zeros(len(spheres), sphere_dtype)
+    for k, (c, r, m) in enumerate(spheres):
+        s[k] = (c, r, m)
+    t = np.zeros(len(tris), triangle_dtype)
+    for k, (v0, v1, v2, m) in enumerate(tris):
+        t[k] = (v0, v1, v2, m)
+    ms = np.zeros(len(mspheres), msphere_dtype)
+    for k, (c0, c1, t0, t1, r, m) in enumerate(mspheres):
+        ms[k] = (c0, c1, t0, t1, r, m)
+    if cam is None:
+        cam = camera_derive((0, 1, 6), (0, 0.5, 0), (0, 1, 0), 35.0, 1.5, 0.05, 6.0, *shutter)
+    return SceneArrays(cam, mats, s, ms, t)
+
+
+def random_rays(n, seed=0):
+    rng = np.random.default_rng(seed)
+    r = np.zeros((n, 7), np.float32)
+    r[:, 0:3] = rng.uniform(-4, 4, size=(n, 3))
+    r[:, 3:6] = rng.normal(size=(n, 3))
+    r[:, 6] = rng.uniform(0, 1, size=n)
+    return r
+
+
+def check_all_paths_agree(ctx, scene, rays):
+    ctx.set_scene(scene, use_bvh=True)
+    orc = Oracle(scene)
+    a = ctx.trace(rays, 0.001, "bvh", want_rec=True)
+    b = ctx.trace(rays, 0.001, "scan", want_rec=True)
+    o = orc.trace(rays, 0.001, "bvh", want_rec=True)
+    for x, y, z in zip(a, b, o):
+        assert x.tobytes() == y.tobytes() == z.tobytes()
+    got, want = ctx.bvh_arrays(), orc.bvh_arrays()
+    for k in ("morton", "perm", "left", "right", "parent"):
+        assert np.array_equal(got[k], want[k]), k
+    return a
+
+
+def test_single_primitive_scenes(ctx):
+    for scene in (make_scene(spheres=[((0, 0.5, 0), 1.0, 0)]),
+                  make_scene(tris=[((-1, 0, 0), (1, 0, 0), (0, 2, 0), 1)]),
+                  make_scene(mspheres=[((0, 0, 0), (1, 1, 0), 0.0, 1.0, 0.7, 2)], shutter=(0.0, 1.0))):
+        ids, t, rec = check_all_paths_agree(ctx, scene, random_rays(4000, 1))
+        assert (ids >= 0).any() and (ids < 0).any()
+        img, st = ctx.render(48, 32, 4, 50, seed=3, count_rays=True)
+        ref, _, cnt = Oracle(scene).render(48, 32, 4, 50, 3)
+        assert st["paths"] == cnt["paths"] and abs(st["rays"] - cnt["rays"]) <= 0.02 * cnt["rays"]
+        assert np.mean(np.abs(np.sqrt(img / 4) - np.sqrt(ref / 4)).max(axis=2) < 1e-3) > 0.97
+
+
+def test_two_and_three_primitives_and_coincident_centroids(ctx):
+    # identical centroids -> identical Morton codes -> the index tie-break of the 64-bit key decides the order
+    same = [((0, 0, 0), 1.0, 0), ((0, 0, 0), 0.5, 1), ((0, 0, 0), 0.25, 2)]
+    check_all_paths_agree(ctx, make_scene(spheres=same[:2]), random_rays(3000, 2))
+    check_all_paths_agree(ctx, make_scene(spheres=same), random_rays(3000, 3))
+    # exact duplicates: the tie rule of the flat scan (last sphere wins, hittable_list.h + sphere.h:45-48)
+    dup = [((0, 0, 0), 1.0, 0)] * 4
+    ids, t, _ = check_all_paths_agree(ctx, make_scene(spheres=dup), random_rays(3000, 4))
+    assert set(np.unique(ids)) <= {-1, 3}
+    # duplicate triangles: exclusive range (triangle.h:61) -> the first one wins
+    tri = [((-2, -2, 0), (2, -2, 0), (0, 2, 0), 0)] * 3
+    ids, t, _ = check_all_paths_agree(ctx, make_scene(tris=tri), random_rays(3000, 5))
+    assert set(np.unique(ids)) <= {-1, 0}
+
+
+def test_degenerate_triangle_is_never_hit(ctx):
+    scene = make_scene(spheres=[((0, 0, -3), 1.0, 0)], tris=[((0, 0, 0), (0, 0, 0), (0, 0, 0), 0), ((0, 0, 0), (1, 1, 1), (2, 2, 2), 0)])
+    ids, t, _ = check_all_paths_agree(ctx, scene, random_rays(5000, 6))
+    assert not np.isin(ids, [1, 2]).any()
+
+
+def test_rays_from_inside_and_axis_aligned(ctx):
+    scene = make_scene(spheres=[((0, 0, 0), 2.0, 2), ((0, 0, 0), 1000.0, 0)])
+    rays = random_rays(2000, 7)
+    rays[:, 0:3] *= 0.2  # origins inside both spheres: the far root is the hit
+    rays[:500, 3:6] = 0
+    rays[:500, 3] = 1  # direction with two exactly-zero components (1/0 = inf in the slab test)
+    rays[500:1000, 3:6] = (0, -1, 0)
+    ids, t, rec = check_all_paths_agree(ctx, scene, rays)
+    assert (ids == 0).all() and np.all(t > 0) and np.all(rec[:, 6] == 0)  # hits from inside: front_face false
+
+
+def test_depth_limits_and_tiny_images(ctx):
+    scene = make_scene(spheres=[((0, 0.5, 0), 1.0, 0), ((0, -100.5, 0), 100.0, 0)])
+    ctx.set_scene(scene)
+    img, st = ctx.render(64, 40, 8, 0, seed=1, count_rays=True)  # depth 0: the loop never runs (rrt.cu:47)
+    assert not img.any() and st["rays"] == 0
+    img1, st1 = ctx.render(64, 40, 8, 1, seed=1, count_rays=True)  # depth 1: only primary rays that see the sky carry light
+    assert st1["rays"] == 64 * 40 * 8
+    ref1, _, cnt1 = Oracle(scene).render(64, 40, 8, 1, 1)
+    assert np.allclose(img1, ref1, atol=1e-4) and cnt1["rays"] == st1["rays"]
+    for (w, h, spp) in ((2, 2, 1), (9, 5, 3), (8, 4, 1), (33, 17, 2)):
+        for sched in (1, 2):
+            img, st = ctx.render(w, h, spp, 50, seed=9, scheduler=sched, count_rays=True)
+            ref, _, cnt = Oracle(scene).render(w, h, spp, 50, 9)
+            assert img.shape == (h, w, 3) and st["paths"] == w * h * spp
+            assert np.mean(np.abs(img - ref).max(axis=2) < 1e-3 * spp) > 0.9
+
+
+def test_camera_only_update(ctx):
+    scene = make_scene(spheres=[((0, 0.5, 0), 1.0, 0), ((2, 0.5, 0), 1.0, 1), ((0, -100.5, 0), 100.0, 0)])
+    cam2 = camera_derive((3, 2, 5), (0, 0.5, 0), (0, 1, 0), 40.0, 1.5, 0.0, 6.0)
+    ctx.set_scene(scene)
+    ctx.set_camera(cam2)
+    a, _ = ctx.render(60, 40, 4, 50, seed=2)
+    ctx.set_scene(SceneArrays(cam2, scene.materials, scene.spheres), use_bvh=True)
+    b, _ = ctx.render(60, 40, 4, 50, seed=2)
+    assert a.tobytes() == b.tobytes()
+
+
+def test_error_paths(built_lib):
+    from rrt_b200 import Context, RrtbError
+
+    with Context(0) as c:
+        with pytest.raises(RrtbError) as e:
+            c.render(16, 16, 1)
+        assert e.value.status == -4  # RRTB_ERR_NO_SCENE
+        scene = make_scene(spheres=[((0, 0, 0), 1.0, 0)])
+        bad = SceneArrays(scene.camera, scene.materials, scene.spheres.copy())
+        bad.spheres["material"] = 7
+        with pytest.raises(RrtbError) as e:
+            c.set_scene(bad)
+        assert e.value.status == -1
+        with pytest.raises(RrtbError):
+            c.set_scene(SceneArrays(scene.camera, scene.materials))  # no objects (scene.h:439-442)
+        c.set_scene(scene)
+        for args in ((1, 16, 1), (16, 16, 0)):
+            with pytest.raises(RrtbError) as e:
+                c.render(*args)
+            assert e.value.status == -1
+        with pytest.raises(RrtbError):
+            c.render(16, 16, 1, rank=3, world=2)
+    with pytest.raises(RrtbError) as e:
+        Context(99)
+    assert e.value.status == -2
+
+
+def test_python_rrt_class_mirror(built_lib):
+    """`Rrt(w, h, spp, depth, use_bvh, tx, ty).render(scene)` -- the reference's seam (rrt.h:14-48)."""
+    from rrt_b200 import Rrt
+
+    scene = make_scene(spheres=[((0, 0.5, 0), 1.0, 0), ((0, -100.5, 0), 100.0, 0)])
+    r = Rrt(40, 24, 3, 50, True, 16, 16)
+    fb = r.render(scene)
+    assert fb.shape == (24, 40, 3) and fb.dtype == np.float32 and r.stats["paths"] == 40 * 24 * 3
+    fb2 = Rrt(40, 24, 3, 50, False).render(scene)  # -b: flat scan, identical image
+    assert fb.tobytes() == fb2.tobytes()
+    assert fb[-1].mean() > fb[0].mean() * 0.5  # row 0 is the BOTTOM scanline (ground), the top rows see sky
