@@ -139,8 +139,9 @@ void orc_camera_ray(const rrtb_camera *cam, int W, int H, int pixel, int sample,
     uint32_t b0[4];
     rng_block(seed, (uint32_t)pixel, (uint32_t)sample, 0u, b0);
     int i = pixel % W, j = pixel / W;
-    float u = ((float)i + orc_u01(b0[0])) / (float)(W - 1);
-    float v = ((float)j + orc_u01(b0[1])) / (float)(H - 1);
+    /* rrt.cu:112-113 divides by (W-1); both sides multiply by the correctly rounded reciprocal instead */
+    float u = ((float)i + orc_u01(b0[0])) * (1.0f / (float)(W - 1));
+    float v = ((float)j + orc_u01(b0[1])) * (1.0f / (float)(H - 1));
     f3 offset = F3(0.f, 0.f, 0.f);
     if (cam->lens_radius > 0.0f) {
         float r = sqrtf(orc_u01(b0[2])) * cam->lens_radius;

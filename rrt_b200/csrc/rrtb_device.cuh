@@ -49,6 +49,7 @@ struct DeviceScene {
 struct DeviceCamera { // rrtb_camera, by value in kernel params (constant bank)
     float origin[3], llc[3], horizontal[3], vertical[3], u[3], v[3], w[3];
     float lens_radius, time0, time1;
+    float inv_w1, inv_h1; // 1 / (W - 1), 1 / (H - 1)
 };
 
 struct Ray {
@@ -108,8 +109,9 @@ __device__ __forceinline__ Ray camera_ray(const DeviceCamera &cam, int W, int H,
 {
     const int pixel = j * W + i;
     uint4 b0 = philox4x32_10(make_uint4((uint32_t)pixel, (uint32_t)sample, 0u, 0u), key);
-    float u = __fdiv_rn(__fadd_rn((float)i, u01(b0.x)), (float)(W - 1));
-    float v = __fdiv_rn(__fadd_rn((float)j, u01(b0.y)), (float)(H - 1));
+    // u = (i + xi) / (W - 1) (rrt.cu:112) as a multiplication by the host-computed reciprocal
+    float u = __fmul_rn(__fadd_rn((float)i, u01(b0.x)), cam.inv_w1);
+    float v = __fmul_rn(__fadd_rn((float)j, u01(b0.y)), cam.inv_h1);
     float ofx = 0.f, ofy = 0.f, ofz = 0.f;
     if (cam.lens_radius > 0.0f) {
         float r = __fmul_rn(__fsqrt_rn(u01(b0.z)), cam.lens_radius);

@@ -68,7 +68,7 @@ void free_scene(rrtb_ctx *ctx);
 
 // rrtb_render.cu
 DeviceScene device_scene(const rrtb_ctx *ctx);
-DeviceCamera device_camera(const rrtb_camera &c);
+DeviceCamera device_camera(const rrtb_camera &c, int W, int H);
 int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum, rrtb_stats *stats);
 int launch_resolve(rrtb_ctx *ctx, const uint64_t *d_accum, float *d_out, size_t n);
 int launch_accumulate(rrtb_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t n);

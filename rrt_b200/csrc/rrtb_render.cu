@@ -328,9 +328,11 @@ DeviceScene device_scene(const rrtb_ctx *ctx)
     return s;
 }
 
-DeviceCamera device_camera(const rrtb_camera &c)
+DeviceCamera device_camera(const rrtb_camera &c, int W, int H)
 {
     DeviceCamera d;
+    d.inv_w1 = 1.0f / (float)(W - 1);
+    d.inv_h1 = 1.0f / (float)(H - 1);
     for (int k = 0; k < 3; ++k) {
         d.origin[k] = c.origin[k];
         d.llc[k] = c.lower_left_corner[k];
@@ -387,7 +389,7 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
 {
     RenderArgs a;
     a.scene = device_scene(ctx);
-    a.cam = device_camera(ctx->cam);
+    a.cam = device_camera(ctx->cam, p->width, p->height);
     a.W = p->width;
     a.H = p->height;
     a.spp = p->spp;
@@ -516,7 +518,7 @@ int launch_camera_rays(rrtb_ctx *ctx, const rrtb_render_params *p, const int32_t
 {
     if (n <= 0) return RRTB_OK;
     uint2 key = make_uint2((uint32_t)p->seed, (uint32_t)(p->seed >> 32));
-    k_camera_rays<<<(n + 127) / 128, 128, 0, ctx->stream>>>(device_camera(ctx->cam), p->width, p->height, key, d_pix, n,
+    k_camera_rays<<<(n + 127) / 128, 128, 0, ctx->stream>>>(device_camera(ctx->cam, p->width, p->height), p->width, p->height, key, d_pix, n,
                                                              sample, d_rays7);
     RRTB_CUDA(ctx, cudaGetLastError());
     return RRTB_OK;
