@@ -253,3 +253,30 @@ def test_cli_drop_in(tmp_path, built_lib):
     r = subprocess.run([exe, "-i", scene_path, "-w", "16", "-h", "8", "-s", "1"], capture_output=True, text=True, timeout=300)
     lines = r.stdout.split("\n")
     assert lines[0] == "P3" and lines[1] == "16 8" and lines[2] == "255" and len(lines) >= 3 + 16 * 8
+
+
+@pytest.mark.slow
+def test_psnr_vs_rrtd_full_size_live(ctx, tmp_path):
+    """The north-star bar verbatim: PSNR >= 40 dB against the reference `rrtd` (rrt.cu, double, rebuilt for
+    sm_100a by oracle/Makefile) render of scenes/final.txt at 1200x800, 500 spp, executed on this very box."""
+    from PIL import Image
+
+    from oracle_lib import REF_DIR, ref_scene_path
+    from rrt_b200 import Scene, tonemap
+
+    exe = os.path.join(REF_DIR, "rrtd")
+    scene_path = ref_scene_path("final.txt")
+    if not (os.path.exists(exe) and scene_path):
+        pytest.skip("oracle/_ref/rrtd or the scene text is not staged")
+    W, H, spp = 1200, 800, 500
+    out = tmp_path / "rrtd.png"
+    r = subprocess.run([exe, "-i", scene_path, "-w", str(W), "-h", str(H), "-s", str(spp), "-d", "50", "-o", str(out)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-500:]
+    ref = np.asarray(Image.open(out).convert("RGB"))
+    ctx.set_scene(Scene.from_file(scene_path, W, H), use_bvh=True)
+    img, st = ctx.render(W, H, spp, 50, seed=1984)
+    ours = tonemap(img, spp)
+    val = psnr(ours, ref)
+    print("PSNR vs rrtd (final.txt 1200x800 500 spp): %.2f dB; rrtd stats: %s" % (val, [l for l in r.stderr.splitlines() if l.startswith("stats,")]))
+    assert val >= 40.0, val
