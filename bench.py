@@ -38,6 +38,8 @@ WORKLOADS = {  # BASELINE.json configs[1..4]; configs[0] is the reference's own 
     "final": dict(W=1200, H=800, spp=500, label="scenes/final.txt", config="BASELINE.json configs[1]", data="reference scene file scenes/final.txt"),
     "test3": dict(W=1920, H=1080, spp=256, label="scenes/test3.txt (motion blur)", config="BASELINE.json configs[2]", data="reference scene file scenes/test3.txt"),
     "test2": dict(W=1920, H=1080, spp=256, label="scenes/test2.txt (triangles)", config="BASELINE.json configs[3]", data="reference scene file scenes/test2.txt"),
+    "final_anim": dict(W=1280, H=720, spp=50, label="scenes/final_anim (261 camera-only frames of final.txt)", config="SURVEY 8f2; reference scenes/final_anim/Makefile:9-10",
+                       data="reference scene file scenes/final.txt + the camera path of scenes/final_anim/anim.py"),
     "synthetic": dict(W=3840, H=2160, spp=1024, label="synthetic 1 003 520 triangles + 100 004 spheres", config="BASELINE.json configs[4]",
                       data="synthetic scene generated in the reference grammar (rrt_b200/synthetic.py, seed 20221005)"),
     "synthetic_small": dict(W=3840, H=2160, spp=64, label="synthetic 250 880 triangles + 20 004 spheres", config="scaled-down sibling of configs[4]",
@@ -262,6 +264,94 @@ def cpu_baseline_sample(rays_per_path):
             "sample": "oracle port (OpenMP) final.txt %dx%d, %d spp, %.2f s" % (W, H, spp, sec)}
 
 
+def run_anim(args, wl, rank, world, local_rank):
+    """--workload final_anim: the reference's 261-frame camera dolly (1280x720, 50 spp) as ONE uploaded scene +
+    one camera update and one kernel launch per frame; frames dealt round-robin over the ranks (no collective).
+    A step = the whole animation."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from rrt_b200 import Context
+    from rrt_b200.anim import final_anim_cameras, frames_of_rank
+
+    Wl, Hl, spp = args.width or wl["W"], args.height or wl["H"], (args.spp if args.spp != SPP else wl["spp"])
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(local_rank)
+    scene, src = load_workload("final", Wl, Hl)
+    cams = final_anim_cameras(Wl, Hl)
+    mine = frames_of_rank(len(cams), rank, world)
+    ctx = Context(local_rank)
+    ctx.set_scene(scene, use_bvh=True)
+    n = 3 * Wl * Hl
+    acc = torch.zeros(n, dtype=torch.int64, device=dev)
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    host = np.empty((Hl, Wl, 3), np.float32)
+    params = ctx.params(Wl, Hl, spp, DEPTH, SEED)
+    pcount = ctx.params(Wl, Hl, spp, DEPTH, SEED, count_rays=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(p=params):
+        rays = 0
+        for f in mine:
+            ctx.set_camera(cams[f])
+            acc.zero_()
+            torch.cuda.synchronize()
+            st = ctx.render_device(p, acc.data_ptr())
+            rays += st["rays"]
+            ctx.resolve_device(acc.data_ptr(), out.data_ptr(), n)
+        return rays
+
+    rays = torch.tensor([step(pcount)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(rays)
+    total_rays = int(rays.item())
+    for _ in range(max(args.warmup - 1, 0)):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = t.item() / args.steps
+    # e2e: host framebuffer per frame through rrtb_render (D2H inside), scene uploaded once per step
+    barrier()
+    t0 = time.perf_counter()
+    ctx.set_scene(scene, use_bvh=True)
+    for f in mine:
+        ctx.set_camera(cams[f])
+        ctx.render(Wl, Hl, spp, DEPTH, SEED, out=host)
+    barrier()
+    e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s on %s" % wl["label"], "value": total_rays / sec / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (f64 leaf discriminants, u64 fixed-point accumulation)", "data": "%s (%s)" % (wl["data"], src),
+            "config": {"workload": "%s %dx%d, %d spp, depth 50 (%s)" % (wl["label"], Wl, Hl, spp, wl["config"]), "frames": len(cams),
+                       "frames_per_s": len(cams) / sec, "sharding": "frames round-robin over %d GPU(s), no collective" % world,
+                       "rays_per_step": total_rays, "reference": "README of scenes/final_anim: 3.3 hours for the same 261 frames (author's GPU)"},
+            "e2e": {"value": total_rays / e.item() / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(scene.spheres.nbytes + scene.materials.nbytes + 96 * len(cams)),
+                    "d2h_bytes_per_step": int(host.nbytes * len(cams)), "seconds_per_animation": e.item()},
+            "gpu_launches": args.steps * 2 * len(cams),
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -296,6 +386,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.workload == "final_anim":
+        return run_anim(args, WORKLOADS[args.workload], rank, world, local_rank)
     wl = WORKLOADS[args.workload]
     Wl, Hl = args.width or wl["W"], args.height or wl["H"]
     spp = args.spp if (args.spp != SPP or args.workload == "final") else wl["spp"]

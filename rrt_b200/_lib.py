@@ -9,7 +9,7 @@ import os
 from .types import RenderParams, Stats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librrtb200.so")
+LIB_PATH = os.environ.get("RRTB_LIB") or os.path.join(_HERE, "librrtb200.so")  # RRTB_LIB: tuning aid (variant builds)
 
 # every symbol include/rrtb.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [

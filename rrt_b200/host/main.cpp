@@ -3,6 +3,7 @@
 // Same command line, same stdout/stderr protocol and same exit codes as the reference's main.cpp:
 //   flags            -i -o -w -h -s -d -b -tx -ty -q -D          (reference main.cpp:69-119; -h is HEIGHT)
 //   additions        -S <seed>  (Philox key, default 1984 = the reference's curand seed, rrt.cu:88)
+//                    -I <list>  frame batch (reference README.md:64 to-do "input list of scenes to render")
 //   usage + exit 1   on any unknown argument                       (main.cpp:33-51)
 //   exit 1 "no scene loaded" / 2 cannot open / 3 unknown material / 4 missing camera|materials|objects
 //                                                                  (main.cpp:126-127, scene.h:220-223,287-290,431-442)
@@ -14,6 +15,7 @@
 #include <climits>
 #include <cstring>
 #include <iomanip>
+#include <fstream>
 #include <iostream>
 #include <string>
 #include <unistd.h>
@@ -53,7 +55,92 @@ static void usage(const char *argv)
     std::cerr << "  -q                  : query devices & cuda info\n";
     std::cerr << "  -D <device number>  : use this cuda device (0)\n";
     std::cerr << "  -S <seed>           : random seed (1984)\n";
+    std::cerr << "  -I list.txt         : frame batch: one '<scene.txt> <out.png>' per line; scenes that differ only\n";
+    std::cerr << "                        in their camera reuse the uploaded scene and its BVH\n";
     std::exit(1);
+}
+
+// same primitives and materials (camera may differ)?
+static bool same_geometry(const rrtb_scene *a, const rrtb_scene *b)
+{
+    int32_t ca[6], cb[6];
+    rrtb_scene_counts(a, ca);
+    rrtb_scene_counts(b, cb);
+    for (int k = 0; k < 4; ++k)
+        if (ca[k] != cb[k]) return false;
+    const rrtb_camera *cam_a = rrtb_scene_camera(a), *cam_b = rrtb_scene_camera(b);
+    if (ca[2] > 0 && (cam_a->time0 != cam_b->time0 || cam_a->time1 != cam_b->time1)) return false; // moving-sphere boxes span the shutter
+    return memcmp(rrtb_scene_materials(a), rrtb_scene_materials(b), sizeof(rrtb_material) * ca[0]) == 0 &&
+           (ca[1] == 0 || memcmp(rrtb_scene_spheres(a), rrtb_scene_spheres(b), sizeof(rrtb_sphere) * ca[1]) == 0) &&
+           (ca[2] == 0 || memcmp(rrtb_scene_mspheres(a), rrtb_scene_mspheres(b), sizeof(rrtb_msphere) * ca[2]) == 0) &&
+           (ca[3] == 0 || memcmp(rrtb_scene_triangles(a), rrtb_scene_triangles(b), sizeof(rrtb_triangle) * ca[3]) == 0);
+}
+
+static rrtb_scene *load_scene_or_exit(const std::string &filename, int w, int h, bool verbose)
+{
+    rrtb_scene *sc = nullptr;
+    int code = 0;
+    char err[512];
+    if (rrtb_scene_parse_file(filename.c_str(), w, h, &sc, &code, err, sizeof(err)) != RRTB_OK) {
+        std::cerr << err << std::endl;
+        std::exit(code);
+    }
+    if (verbose) {
+        int32_t c[6];
+        rrtb_scene_counts(sc, c);
+        std::cerr << "read scene file: " << filename << "\n";
+        std::cerr << "material count:  " << c[0] << "\n";
+        std::cerr << "sphere count:    " << c[1] << std::endl;
+        std::cerr << "msphere count:   " << c[2] << std::endl;
+        std::cerr << "obj count:       " << c[4] << std::endl;
+        std::cerr << "obj_inst count:  " << c[5] << std::endl;
+        const rrtb_camera *cam = rrtb_scene_camera(sc);
+        if (cam->time0 != cam->time1) std::cerr << "camera time:     " << cam->time0 << " - " << cam->time1 << std::endl;
+    }
+    return sc;
+}
+
+// -I list: "<scene.txt> <out.png>" per line, one context, geometry uploaded only when it changes
+static int run_batch(const std::string &list, int w, int h, int spp, int depth, bool use_bvh, int tx, int ty, int device,
+                     unsigned long long seed)
+{
+    std::ifstream fl(list);
+    if (!fl.good()) {
+        std::cerr << "ERROR: problem with opening file: " << list << "\n";
+        return 2;
+    }
+    Rrt rrt(w, h, spp, depth, use_bvh, tx, ty, device, seed);
+    rrtb_scene *prev = nullptr;
+    std::string scene_file, png_file;
+    std::vector<uint8_t> rgb((size_t)w * h * 3);
+    int frames = 0, uploads = 0;
+    double seconds = 0.0;
+    unsigned long long rays = 0;
+    while (fl >> scene_file >> png_file) {
+        rrtb_scene *cur = load_scene_or_exit(scene_file, w, h, false);
+        vec3 *fb;
+        if (prev && same_geometry(prev, cur)) {
+            fb = rrt.render_camera_only(cur);
+        }
+        else {
+            fb = rrt.render(cur);
+            ++uploads;
+        }
+        seconds += rrt.stats.seconds_render;
+        rays += rrt.stats.rays;
+        rrtb_tonemap_rgb8(&fb[0].e[0], w, h, spp, rgb.data());
+        if (rrtb_write_png(png_file.c_str(), w, h, rgb.data()) != RRTB_OK) {
+            std::cerr << "ERROR: could not write " << png_file << std::endl;
+            return 1;
+        }
+        if (prev) rrtb_scene_free(prev);
+        prev = cur;
+        ++frames;
+    }
+    if (prev) rrtb_scene_free(prev);
+    std::cerr << "batch: " << frames << " frames, " << uploads << " scene uploads, " << seconds << " render seconds, "
+              << (seconds > 0 ? rays / seconds * 1e-6 : 0.0) << " Mrays/s\n";
+    return 0;
 }
 
 int main(int argc, char *argv[])
@@ -66,6 +153,7 @@ int main(int argc, char *argv[])
     bool use_bvh = true;
     int device = 0;
     unsigned long long seed = 1984;
+    std::string batch_list;
 
     // Only the first letter after '-' is examined, as in the reference (so "-input" == "-i").
     for (int i = 1; i < argc; ++i) {
@@ -90,8 +178,13 @@ int main(int argc, char *argv[])
         else if (c == 'q') query_cuda_info();
         else if (c == 'D') device = atoi(next());
         else if (c == 'S') seed = strtoull(next(), nullptr, 10);
+        else if (c == 'I') batch_list = next();
         else usage(argv[i]);
     }
+
+    if (batch_list != "")
+        return run_batch(batch_list, image_width, image_height, num_samples, max_depth, use_bvh, num_threads_x, num_threads_y,
+                         device, seed);
 
     rrtb_scene *the_scene = nullptr;
     if (the_scene_filename != "") {

@@ -46,6 +46,19 @@ class Rrt {
     vec3 *render(const rrtb_scene *the_scene)
     {
         rrtb_check(rrtb_scene_upload(ctx, the_scene, bvh ? 1 : 0), ctx, "rrtb_scene_upload");
+        return render_uploaded();
+    }
+
+    // Frame batches (reference README to-do "input list of scenes to render", README.md:64): a scene that
+    // differs from the uploaded one only in its camera keeps the uploaded primitives and LBVH.
+    vec3 *render_camera_only(const rrtb_scene *the_scene)
+    {
+        rrtb_check(rrtb_camera_set(ctx, rrtb_scene_camera(the_scene)), ctx, "rrtb_camera_set");
+        return render_uploaded();
+    }
+
+    vec3 *render_uploaded()
+    {
         fb.resize((size_t)image_width * image_height);
         rrtb_render_params p{};
         p.width = image_width;

@@ -1,0 +1,69 @@
+"""Frame batches: camera-only animation with ONE uploaded scene.  A frame rendered through
+rrtb_camera_set is bit-identical to the same frame rendered alone, in the Python binding and in the CLI's
+-I batch mode; frames deal round-robin across ranks without any collective."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from rrt_b200.types import SceneArrays
+
+
+def test_frames_of_rank_partition():
+    from rrt_b200.anim import frames_of_rank
+
+    for world in (1, 2, 3, 8):
+        got = sorted(f for r in range(world) for f in frames_of_rank(261, r, world))
+        assert got == list(range(261))
+
+
+@pytest.mark.gpu
+def test_camera_only_frames_equal_standalone_frames(ctx):
+    from rrt_b200.anim import final_anim_cameras, render_frames
+
+    scene, _ = load_golden("final")
+    W, H, spp = 160, 90, 4
+    cams = final_anim_cameras(W, H, n_frames=261)
+    pick = [0, 130, 260]
+    ctx.set_scene(scene, use_bvh=True)
+    frames = {}
+    render_frames(ctx, [cams[i] for i in pick], W, H, spp, on_frame=lambda f, img, st: frames.__setitem__(pick[f], img.copy()))
+    for i in pick:
+        ctx.set_scene(SceneArrays(cams[i], scene.materials, scene.spheres), use_bvh=True)
+        alone, _ = ctx.render(W, H, spp, 50, 1984)
+        assert alone.tobytes() == frames[i].tobytes()
+    assert frames[0].tobytes() != frames[260].tobytes()
+    # frame 0 is the camera of scenes/final.txt itself (13 2 3 -> 0 0 0, vfov 30, aperture 0.1, focus 10 vs |from| = 13.49)
+    assert np.allclose(cams[0]["origin"][0], (13, 2, 3))
+
+
+@pytest.mark.gpu
+def test_cli_batch_mode(tmp_path, built_lib):
+    from PIL import Image
+
+    from oracle_lib import ref_scene_path
+
+    exe = os.path.join(ROOT, "rrt_b200", "bin", "rrt")
+    base = ref_scene_path("final.txt")
+    if not (os.path.exists(exe) and base):
+        pytest.skip("drop-in executable or scene text not staged")
+    body = [l for l in open(base).read().splitlines() if not l.startswith("camera")]
+    lines = []
+    for k, x in enumerate((13.0, 9.5, 6.0)):
+        p = tmp_path / ("z_%03d.txt" % k)
+        p.write_text("camera %g 2 3  0 0 0  0 1 0  30.0 0.1 %g\n" % (x, (x * x + 13) ** 0.5) + "\n".join(body) + "\n")
+        lines.append("%s %s" % (p, tmp_path / ("z_%03d.png" % k)))
+    other = ref_scene_path("test1.txt")
+    lines.append("%s %s" % (other, tmp_path / "t1.png"))
+    (tmp_path / "list.txt").write_text("\n".join(lines) + "\n")
+    args = ["-w", "96", "-h", "64", "-s", "4"]
+    r = subprocess.run([exe, "-I", str(tmp_path / "list.txt")] + args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "batch: 4 frames, 2 scene uploads" in r.stderr  # 3 camera-only frames share one upload, test1 is another
+    for k in range(3):
+        single = tmp_path / ("single_%d.png" % k)
+        r = subprocess.run([exe, "-i", str(tmp_path / ("z_%03d.txt" % k)), "-o", str(single)] + args, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0
+        assert np.array_equal(np.asarray(Image.open(single)), np.asarray(Image.open(tmp_path / ("z_%03d.png" % k))))
