@@ -63,7 +63,6 @@ int cuda_fail(rrtb_ctx *ctx, cudaError_t e, const char *expr, const char *file, 
     } while (0)
 
 // rrtb_bvh.cu
-int build_acceleration(rrtb_ctx *ctx);
 void free_scene(rrtb_ctx *ctx);
 
 // rrtb_render.cu

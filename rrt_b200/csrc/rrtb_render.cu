@@ -82,9 +82,9 @@ __global__ void __launch_bounds__(RENDER_TPB, 2) k_render(const RenderArgs a)
                 else {
                     // item = (local_tile * n_chunks + chunk) * 32 + pixel_in_tile
                     unsigned pit = (unsigned)(item & 31ull);
-                    unsigned long long tc = item >> 5;
-                    int chunk = (int)(tc % (unsigned long long)a.n_chunks);
-                    int ltile = (int)(tc / (unsigned long long)a.n_chunks);
+                    unsigned long long tile_chunk = item >> 5;
+                    int chunk = (int)(tile_chunk % (unsigned long long)a.n_chunks);
+                    int ltile = (int)(tile_chunk / (unsigned long long)a.n_chunks);
                     int tile = a.shard_mode == RRTB_SHARD_TILES ? ltile * a.world + a.rank : ltile;
                     int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
                     int i = tx * 8 + (int)(pit & 7u), j = ty * 4 + (int)(pit >> 3);

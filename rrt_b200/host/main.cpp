@@ -4,6 +4,8 @@
 //   flags            -i -o -w -h -s -d -b -tx -ty -q -D          (reference main.cpp:69-119; -h is HEIGHT)
 //   additions        -S <seed>  (Philox key, default 1984 = the reference's curand seed, rrt.cu:88)
 //                    -I <list>  frame batch (reference README.md:64 to-do "input list of scenes to render")
+//                    -G <n>     n GPUs of this box: one context + one host thread per GPU, each renders its
+//                               interleaved tiles; the shards are disjoint, so summing them is exact
 //   usage + exit 1   on any unknown argument                       (main.cpp:33-51)
 //   exit 1 "no scene loaded" / 2 cannot open / 3 unknown material / 4 missing camera|materials|objects
 //                                                                  (main.cpp:126-127, scene.h:220-223,287-290,431-442)
@@ -15,8 +17,12 @@
 #include <climits>
 #include <cstring>
 #include <iomanip>
+#include <algorithm>
 #include <fstream>
 #include <iostream>
+#include <memory>
+#include <thread>
+#include <vector>
 #include <string>
 #include <unistd.h>
 
@@ -55,6 +61,7 @@ static void usage(const char *argv)
     std::cerr << "  -q                  : query devices & cuda info\n";
     std::cerr << "  -D <device number>  : use this cuda device (0)\n";
     std::cerr << "  -S <seed>           : random seed (1984)\n";
+    std::cerr << "  -G <n>              : render on n GPUs (devices D..D+n-1), interleaved 8x4-pixel tiles (1)\n";
     std::cerr << "  -I list.txt         : frame batch: one '<scene.txt> <out.png>' per line; scenes that differ only\n";
     std::cerr << "                        in their camera reuse the uploaded scene and its BVH\n";
     std::exit(1);
@@ -154,6 +161,7 @@ int main(int argc, char *argv[])
     int device = 0;
     unsigned long long seed = 1984;
     std::string batch_list;
+    int n_gpus = 1;
 
     // Only the first letter after '-' is examined, as in the reference (so "-input" == "-i").
     for (int i = 1; i < argc; ++i) {
@@ -179,6 +187,7 @@ int main(int argc, char *argv[])
         else if (c == 'D') device = atoi(next());
         else if (c == 'S') seed = strtoull(next(), nullptr, 10);
         else if (c == 'I') batch_list = next();
+        else if (c == 'G') n_gpus = atoi(next());
         else usage(argv[i]);
     }
 
@@ -214,7 +223,13 @@ int main(int argc, char *argv[])
     std::time_t render_time = std::time(nullptr);
     std::tm render_tm = *std::localtime(&render_time);
 
-    Rrt rrt(image_width, image_height, num_samples, max_depth, use_bvh, num_threads_x, num_threads_y, device, seed);
+    // rank 0 renders in this thread; -G n adds n-1 more contexts, one host thread each
+    Rrt rrt(image_width, image_height, num_samples, max_depth, use_bvh, num_threads_x, num_threads_y, device, seed, 0,
+            n_gpus < 1 ? 1 : n_gpus);
+    std::vector<std::unique_ptr<Rrt>> peers;
+    for (int r = 1; r < n_gpus; ++r)
+        peers.emplace_back(new Rrt(image_width, image_height, num_samples, max_depth, use_bvh, num_threads_x, num_threads_y,
+                                   device + r, seed, r, n_gpus));
     std::cerr << "Rendering a " << image_width << "x" << image_height << " image with " << num_samples
               << " samples per pixel on a persistent sm_100a kernel.\n";
     int32_t c[6];
@@ -222,7 +237,19 @@ int main(int argc, char *argv[])
     std::cerr << "num_hittables = " << (c[1] + c[2] + c[3]) << "\n";
     std::cerr << "CUDA Device: " << device << std::endl;
 
+    std::vector<vec3 *> peer_fb(peers.size(), nullptr);
+    std::vector<std::thread> workers;
+    for (size_t r = 0; r < peers.size(); ++r)
+        workers.emplace_back([&, r]() { peer_fb[r] = peers[r]->render(the_scene); });
     vec3 *fb = rrt.render(the_scene);
+    for (auto &w : workers) w.join();
+    for (size_t r = 0; r < peers.size(); ++r) { // shards are disjoint (zeros elsewhere): the sum is exact
+        const size_t n = (size_t)image_width * image_height;
+        for (size_t k = 0; k < n; ++k)
+            for (int ch = 0; ch < 3; ++ch) fb[k].e[ch] += peer_fb[r][k].e[ch];
+        rrt.stats.rays += peers[r]->stats.rays;
+        rrt.stats.seconds_render = std::max(rrt.stats.seconds_render, peers[r]->stats.seconds_render);
+    }
 
     const double timer_seconds = rrt.stats.seconds_render;
     std::cerr << "took " << timer_seconds << " seconds.\n";
@@ -234,7 +261,7 @@ int main(int argc, char *argv[])
               << num_samples << "," << rrt.stats.kernel_launches << "," << num_threads_x << "," << num_threads_y << ","
               << timer_seconds << "," << rrt.stats.rays << ","
               << (timer_seconds > 0 ? rrt.stats.rays / timer_seconds * 1e-6 : 0.0) << "," << rrt.stats.seconds_build
-              << ",1\n";
+              << "," << (n_gpus < 1 ? 1 : n_gpus) << "\n";
 
     if (png_filename == nullptr) {
         // PPM to stdout: rows top-down, one "r g b" line per pixel (main.cpp:140-149)

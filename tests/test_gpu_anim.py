@@ -67,3 +67,29 @@ def test_cli_batch_mode(tmp_path, built_lib):
         r = subprocess.run([exe, "-i", str(tmp_path / ("z_%03d.txt" % k)), "-o", str(single)] + args, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0
         assert np.array_equal(np.asarray(Image.open(single)), np.asarray(Image.open(tmp_path / ("z_%03d.png" % k))))
+
+
+@pytest.mark.gpu
+def test_cli_multi_gpu_is_bit_identical(tmp_path, built_lib):
+    """`rrt -G n`: one context + one host thread per GPU, interleaved tiles; same PNG as one GPU."""
+    import torch
+    from PIL import Image
+
+    from oracle_lib import ref_scene_path
+
+    exe = os.path.join(ROOT, "rrt_b200", "bin", "rrt")
+    p = ref_scene_path("test2.txt")
+    if not (os.path.exists(exe) and p):
+        pytest.skip("drop-in executable or scene text not staged")
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    args = ["-i", p, "-w", "200", "-h", "120", "-s", "8"]
+    outs = []
+    for g in (1, 2, min(n, 8)):
+        out = tmp_path / ("g%d.png" % g)
+        r = subprocess.run([exe] + args + ["-G", str(g), "-o", str(out)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        assert r.stderr.strip().splitlines()[-1].endswith(",%d" % g)  # stats line: GPU count is the last appended field
+        outs.append(np.asarray(Image.open(out)))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
