@@ -188,6 +188,8 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     if ((rc = dev_alloc(ctx, ctx->d_node_box, (size_t)6 * n))) return rc;
     if ((rc = dev_alloc(ctx, ctx->d_visit, (size_t)n))) return rc;
     if ((rc = dev_alloc(ctx, ctx->d_nodes, (size_t)4 * n))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_top_nodes, (size_t)4 * RRTB_TOP_NODES))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_n_top, (size_t)1))) return rc;
     if ((rc = dev_alloc(ctx, ctx->d_leaves, (size_t)3 * n))) return rc;
     if ((rc = dev_alloc(ctx, ctx->d_leaf_info, (size_t)n))) return rc;
     if ((rc = dev_alloc(ctx, ctx->d_reduce, (size_t)nb * 7 + 16))) return rc;

@@ -449,6 +449,41 @@ __global__ void __launch_bounds__(TPB) k_flatten_leaves(const uint64_t *__restri
     leaf_info[k] = info[id];
 }
 
+// The first RRTB_TOP_NODES nodes of the tree in breadth-first order, for staging in shared memory by the
+// render kernel (north_star: "top tree levels staged in shared memory").  Child refs that stay inside the
+// staged set are re-encoded as TOP_FLAG | position; everything else keeps its global encoding.  One thread:
+// the set is tiny (<= 112 nodes) and this runs once per scene.
+__global__ void k_build_top(const float4 *__restrict__ nodes, int n_internal, float4 *__restrict__ top, int *__restrict__ n_top_out)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int queue[RRTB_TOP_NODES];
+    int count = 0;
+    if (n_internal > 0) queue[count++] = 0;
+    for (int i = 0; i < count; ++i) { // breadth-first: append internal children while there is room
+        const float4 n3 = nodes[4 * queue[i] + 3];
+        const int ch[2] = {__float_as_int(n3.x), __float_as_int(n3.y)};
+        for (int c = 0; c < 2; ++c)
+            if (ch[c] >= 0 && count < RRTB_TOP_NODES) queue[count++] = ch[c];
+    }
+    for (int i = 0; i < count; ++i) {
+        const int id = queue[i];
+        float4 n3 = nodes[4 * id + 3];
+        int ch[2] = {__float_as_int(n3.x), __float_as_int(n3.y)};
+        for (int c = 0; c < 2; ++c)
+            if (ch[c] >= 0)
+                for (int q = i + 1; q < count; ++q) // children are always later in breadth-first order
+                    if (queue[q] == ch[c]) {
+                        ch[c] = TOP_FLAG | q;
+                        break;
+                    }
+        top[4 * i + 0] = nodes[4 * id + 0];
+        top[4 * i + 1] = nodes[4 * id + 1];
+        top[4 * i + 2] = nodes[4 * id + 2];
+        top[4 * i + 3] = make_float4(__int_as_float(ch[0]), __int_as_float(ch[1]), 0.f, 0.f);
+    }
+    *n_top_out = count;
+}
+
 // exposed to rrtb_api.cu (scene upload): raw struct arrays are staged by the caller
 int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_msphere *d_msph, const rrtb_triangle *d_tri)
 {
@@ -498,7 +533,9 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
                                          ctx->d_node_box, bc, ctx->d_nodes);
     k_flatten_leaves<<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_prim, ctx->d_prim_info, ctx->d_leaves,
                                          ctx->d_leaf_info);
+    k_build_top<<<1, 32, 0, st>>>(ctx->d_nodes, max(n - 1, 1), ctx->d_top_nodes, ctx->d_n_top);
     RRTB_CUDA(ctx, cudaGetLastError());
+    RRTB_CUDA(ctx, cudaMemcpyAsync(&ctx->n_top, ctx->d_n_top, sizeof(int), cudaMemcpyDeviceToHost, st));
     return RRTB_OK;
 }
 
@@ -511,7 +548,7 @@ void free_scene(rrtb_ctx *ctx)
     F(ctx->d_prim); F(ctx->d_prim_info); F(ctx->d_materials); F(ctx->d_material_type); F(ctx->d_prim_box);
     F(ctx->d_morton); F(ctx->d_keys); F(ctx->d_keys_tmp); F(ctx->d_left); F(ctx->d_right); F(ctx->d_parent);
     F(ctx->d_node_box); F(ctx->d_visit); F(ctx->d_nodes); F(ctx->d_leaves); F(ctx->d_leaf_info); F(ctx->d_reduce);
-    F(ctx->d_hist);
+    F(ctx->d_hist); F(ctx->d_top_nodes); F(ctx->d_n_top);
     ctx->has_scene = false;
 }
 

@@ -36,6 +36,8 @@ enum : int { PRIM_SPHERE = 0, PRIM_MSPHERE = 1, PRIM_TRIANGLE = 2 };
 
 struct DeviceScene {
     const float4 *nodes;     // [4 * max(n-1,1)]
+    const float4 *top_nodes; // [4 * n_top] breadth-first top of the tree, refs re-encoded with TOP_FLAG
+    int n_top;
     const float4 *leaves;    // [3 * n]   leaf order
     const int2 *leaf_info;   // [n]
     const float4 *flat_leaves; // [3 * n]  object-id order (scan mode)
@@ -348,13 +350,25 @@ __device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, 
 // tree is <= 62.
 #define RRTB_STACK 64
 #define TRAV_DONE ((int)0x80000000)
+// internal-node refs with this bit set index the breadth-first "top" copy of the tree that the pool kernel
+// stages in shared memory (node counts are < 2^29, so bit 30 is free)
+#define TOP_FLAG 0x40000000
+#define RRTB_TOP_NODES 112
 
-template <bool COUNT>
+// TOP = true: refs carrying TOP_FLAG are fetched from `top` (shared memory), the others from `nodes` (global)
+template <bool COUNT, bool TOP = false>
 __device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, const RayPre &p, float t_min, float t_max,
-                                          int &cur, int &sp, int *stack, TravCounters &cnt)
+                                          int &cur, int &sp, int *stack, TravCounters &cnt, const float4 *top = nullptr)
 {
-    float4 n0 = __ldg(nodes + 4 * cur), n1 = __ldg(nodes + 4 * cur + 1), n2 = __ldg(nodes + 4 * cur + 2),
-           n3 = __ldg(nodes + 4 * cur + 3);
+    float4 n0, n1, n2, n3;
+    if (TOP && (cur & TOP_FLAG)) {
+        const float4 *q = top + 4 * (cur & ~TOP_FLAG);
+        n0 = q[0]; n1 = q[1]; n2 = q[2]; n3 = q[3];
+    }
+    else {
+        n0 = __ldg(nodes + 4 * cur); n1 = __ldg(nodes + 4 * cur + 1); n2 = __ldg(nodes + 4 * cur + 2);
+        n3 = __ldg(nodes + 4 * cur + 3);
+    }
     float tl, tr;
     if (COUNT) cnt.box += 2;
     bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, p, t_min, t_max, tl);

@@ -39,6 +39,9 @@ struct rrtb_ctx {
     int *d_visit = nullptr;         // [n-1]
     // device: traversal structures
     float4 *d_nodes = nullptr;      // [4*max(n-1,1)]
+    float4 *d_top_nodes = nullptr;  // [4*RRTB_TOP_NODES] breadth-first copy of the top of the tree (smem staging)
+    int *d_n_top = nullptr;
+    int n_top = 0;
     float4 *d_leaves = nullptr;     // [3n] leaf order
     int2 *d_leaf_info = nullptr;    // [n]
     // scratch

@@ -314,6 +314,8 @@ DeviceScene device_scene(const rrtb_ctx *ctx)
 {
     DeviceScene s;
     s.nodes = ctx->d_nodes;
+    s.top_nodes = ctx->d_top_nodes;
+    s.n_top = ctx->n_top;
     s.leaves = ctx->d_leaves;
     s.leaf_info = ctx->d_leaf_info;
     s.flat_leaves = ctx->d_prim;
@@ -363,9 +365,9 @@ static int launch_persistent(rrtb_ctx *ctx, K kernel, const RenderArgs &args, in
 }
 
 template <typename K>
-static int launch_pool(rrtb_ctx *ctx, K kernel, const RenderArgs &args, int *blocks_out)
+static int launch_pool(rrtb_ctx *ctx, K kernel, const RenderArgs &args, int *blocks_out, bool stage_top)
 {
-    const int smem = (int)(sizeof(WarpPool) * POOL_WARPS);
+    const int smem = (int)(sizeof(WarpPool) * POOL_WARPS + (stage_top ? sizeof(float4) * 4 * RRTB_TOP_NODES : 0));
     RRTB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
     RRTB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RENDER_TPB, smem));
@@ -437,7 +439,11 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
         const bool bvh = ctx->use_bvh != 0, cnt = p->count_rays != 0;
         int rc;
         if (bvh && p->scheduler != RRTB_SCHED_SIMPLE) {
-            rc = cnt ? launch_pool(ctx, k_render_pool<true, 2>, a, &blocks) : launch_pool(ctx, k_render_pool<false, 2>, a, &blocks);
+            bool stage_top = false; // option, see rrtb_render_pool.cuh
+            if (const char *e = getenv("RRTB_STAGE_TOP")) stage_top = atoi(e) != 0;
+            if (cnt) rc = launch_pool(ctx, k_render_pool<true, 2, false>, a, &blocks, false);
+            else if (stage_top) rc = launch_pool(ctx, k_render_pool<false, 2, true>, a, &blocks, true);
+            else rc = launch_pool(ctx, k_render_pool<false, 2, false>, a, &blocks, false);
         }
         else if (bvh && cnt) rc = launch_render_t<true, true>(ctx, a, &blocks);
         else if (bvh) rc = launch_render_t<true, false>(ctx, a, &blocks);

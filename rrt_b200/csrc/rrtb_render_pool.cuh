@@ -43,7 +43,7 @@ struct WarpPool { // SoA, one per warp, in dynamic shared memory
     unsigned char gq[POOL]; // gen stack
 };
 
-template <bool COUNT_RAYS, int NODE_UNROLL>
+template <bool COUNT_RAYS, int NODE_UNROLL, bool STAGE_TOP>
 __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -54,6 +54,17 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
     const float4 *__restrict__ nodes = s.nodes;
     const float4 *__restrict__ leaves = s.leaves;
     const int2 *__restrict__ info = s.leaf_info;
+
+    // STAGE_TOP (north_star: "top tree levels staged in shared memory"): the first <= RRTB_TOP_NODES nodes in
+    // breadth-first order sit behind the pools.  Measured on B200 (profiles/README.md) this LOSES 9 % on
+    // final.txt -- the hot top of the tree is L1-resident anyway, the 7 KB come out of L1 and every node
+    // visit pays a shared-or-global branch -- so it is compiled as an option and off by default.
+    float4 *top = reinterpret_cast<float4 *>(smem_raw + sizeof(WarpPool) * POOL_WARPS);
+    if (STAGE_TOP) {
+        for (int k = threadIdx.x; k < 4 * s.n_top; k += RENDER_TPB) top[k] = __ldg(s.top_nodes + k);
+        __syncthreads();
+    }
+    const int root = (STAGE_TOP && s.n_top > 0) ? TOP_FLAG : 0;
 
     // every slot starts on the gen stack with nothing to accumulate
     for (int k = lane; k < POOL; k += 32) {
@@ -96,7 +107,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
                 pre = ray_pre(ray);
                 best.t = __int_as_float(0x7f800000);
                 best.ref = -1;
-                cur = 0;
+                cur = root;
                 sp = 0;
             }
             tq_n -= take;
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
             do {
 #pragma unroll
                 for (int u = 0; u < NODE_UNROLL; ++u) // node visits between two continue-votes
-                    if (cur >= 0) node_step<COUNT_RAYS>(nodes, pre, 0.001f, best.t, cur, sp, stack, tc);
+                    if (cur >= 0) node_step<COUNT_RAYS, STAGE_TOP>(nodes, pre, 0.001f, best.t, cur, sp, stack, tc, top);
             } while (++it < a.step_iters && __popc(__ballot_sync(0xffffffffu, cur >= 0)) >= a.th_node);
             const bool at_leaf = cur < 0 && cur != TRAV_DONE;
             const unsigned leaf_mask = __ballot_sync(0xffffffffu, at_leaf);

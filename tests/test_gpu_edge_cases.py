@@ -162,3 +162,22 @@ def test_python_rrt_class_mirror(built_lib):
     fb2 = Rrt(40, 24, 3, 50, False).render(scene)  # -b: flat scan, identical image
     assert fb.tobytes() == fb2.tobytes()
     assert fb[-1].mean() > fb[0].mean() * 0.5  # row 0 is the BOTTOM scanline (ground), the top rows see sky
+
+
+def test_tree_top_staging_option_gives_the_same_image(ctx, monkeypatch):
+    """RRTB_STAGE_TOP=1 stages the breadth-first top of the LBVH in shared memory (north_star option; off by
+    default because it measured slower on B200, profiles/README.md): the image must not change."""
+    from conftest import load_golden
+
+    scene, _ = load_golden("final")
+    ctx.set_scene(scene, use_bvh=True)
+    a, _ = ctx.render(96, 64, 6, 50, seed=11)
+    monkeypatch.setenv("RRTB_STAGE_TOP", "1")
+    b, _ = ctx.render(96, 64, 6, 50, seed=11)
+    assert a.tobytes() == b.tobytes()
+    tiny = make_scene(spheres=[((0, 0.5, 0), 1.0, 0)])  # single primitive: degenerate one-node tree
+    ctx.set_scene(tiny)
+    c, _ = ctx.render(32, 24, 2, 50, seed=1)
+    monkeypatch.delenv("RRTB_STAGE_TOP")
+    d, _ = ctx.render(32, 24, 2, 50, seed=1)
+    assert c.tobytes() == d.tobytes()
