@@ -149,6 +149,10 @@ typedef struct rrtb_stats {
 /* Host-buffer entry point (what Rrt::render returns, rrt.h:34): renders this context's shard and
  * writes 3*W*H floats (RGB sums) to the HOST buffer out_rgb. Pixels outside the shard are 0. */
 int rrtb_render(rrtb_ctx *ctx, const rrtb_render_params *p, float *out_rgb, rrtb_stats *stats);
+/* The same render handed back as DOUBLE sums -- what the reference's `rrtd` build returns (FP_T = double,
+ * rtweekend.h:20-28; Makefile:36-37).  The 64-bit fixed-point accumulators convert to double exactly, so this is
+ * the framebuffer of the `rrtd` drop-in; rays, RNG and intersection arithmetic are those of rrtb_render. */
+int rrtb_render_f64(rrtb_ctx *ctx, const rrtb_render_params *p, double *out_rgb, rrtb_stats *stats);
 
 /* Device-resident entry points (used by the multi-GPU host and bench.py):
  *   d_accum : DEVICE pointer (this GPU's memory, or a peer GPU's mapped over NVLink) to 3*W*H
@@ -219,6 +223,8 @@ int rrtb_camera_derive(const float lookfrom[3], const float lookat[3], const flo
                        rrtb_camera *out);
 /* color.h:8-23 + the vertical flip of main.cpp:150-163: rgb_sum (bottom-up sums) -> rgb8 (top-down). */
 int rrtb_tonemap_rgb8(const float *rgb_sum, int width, int height, int spp, uint8_t *rgb8);
+/* the same in the double build's arithmetic (FP_T = double in color.h:8-23) */
+int rrtb_tonemap_rgb8_f64(const double *rgb_sum, int width, int height, int spp, uint8_t *rgb8);
 /* PNG writer used where the reference calls stbi_write_png (main.cpp:164). */
 int rrtb_write_png(const char *path, int width, int height, const uint8_t *rgb8);
 

@@ -169,14 +169,19 @@ class Context:
         return RenderParams(int(width), int(height), int(spp), int(max_depth), int(seed), int(rank), int(world),
                             int(shard_mode), 1 if count_rays else 0, int(scheduler), 0)
 
-    def render(self, width, height, spp, max_depth=50, seed=1984, rank=0, world=1, shard_mode=0, count_rays=False, out=None, scheduler=0):
-        """Host-buffer path (what Rrt::render returns): float32 [H, W, 3] SUMS, row 0 = bottom scanline."""
+    def render(self, width, height, spp, max_depth=50, seed=1984, rank=0, world=1, shard_mode=0, count_rays=False, out=None, scheduler=0,
+               dtype=np.float32):
+        """Host-buffer path (what Rrt::render returns): [H, W, 3] SUMS, row 0 = bottom scanline.
+        dtype float32 = the `rrt` framebuffer, float64 = the `rrtd` framebuffer (rrtb_render_f64)."""
         p = self.params(width, height, spp, max_depth, seed, rank, world, shard_mode, count_rays, scheduler)
+        dtype = np.dtype(dtype) if out is None else out.dtype
+        assert dtype in (np.dtype(np.float32), np.dtype(np.float64))
         if out is None:
-            out = np.empty((height, width, 3), np.float32)
-        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == 3 * width * height
+            out = np.empty((height, width, 3), dtype)
+        assert out.flags.c_contiguous and out.size == 3 * width * height
         st = Stats()
-        self._check(self.lib.rrtb_render(self.h, C.byref(p), C.c_void_p(out.ctypes.data), C.byref(st)))
+        fn = self.lib.rrtb_render if dtype == np.dtype(np.float32) else self.lib.rrtb_render_f64
+        self._check(fn(self.h, C.byref(p), C.c_void_p(out.ctypes.data), C.byref(st)))
         return out, st.as_dict()
 
     def render_device(self, params, accum_ptr):
@@ -252,10 +257,11 @@ def camera_derive(lookfrom, lookat, vup, vfov, aspect_ratio, aperture, focus_dis
 def tonemap(rgb_sum, spp):
     """color.h:8-23 + main.cpp:150-163: float sums (bottom-up) -> uint8 [H, W, 3] top-down."""
     lib = _lib.load()
-    rgb_sum = np.ascontiguousarray(rgb_sum, dtype=np.float32)
+    f64 = np.asarray(rgb_sum).dtype == np.float64  # the rrtd framebuffer: color.h with FP_T = double
+    rgb_sum = np.ascontiguousarray(rgb_sum, dtype=np.float64 if f64 else np.float32)
     H, W, _ = rgb_sum.shape
     out = np.zeros((H, W, 3), np.uint8)
-    rc = lib.rrtb_tonemap_rgb8(_vp(rgb_sum), W, H, int(spp), _vp(out))
+    rc = (lib.rrtb_tonemap_rgb8_f64 if f64 else lib.rrtb_tonemap_rgb8)(_vp(rgb_sum), W, H, int(spp), _vp(out))
     if rc != 0:
         raise RrtbError(rc, "rrtb_tonemap_rgb8")
     return out

@@ -311,7 +311,7 @@ int rrtb_accumulate_device(rrtb_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src
     return RRTB_OK;
 }
 
-int rrtb_render(rrtb_ctx *ctx, const rrtb_render_params *p, float *out_rgb, rrtb_stats *stats)
+static int render_host(rrtb_ctx *ctx, const rrtb_render_params *p, void *out_rgb, rrtb_stats *stats, bool f64)
 {
     int rc = check_render(ctx, p);
     if (rc) return rc;
@@ -325,7 +325,7 @@ int rrtb_render(rrtb_ctx *ctx, const rrtb_render_params *p, float *out_rgb, rrtb
         ctx->d_rgb = nullptr;
         ctx->accum_elems = 0;
         RRTB_CUDA(ctx, cudaMalloc((void **)&ctx->d_accum, n * sizeof(unsigned long long)));
-        RRTB_CUDA(ctx, cudaMalloc((void **)&ctx->d_rgb, n * sizeof(float)));
+        RRTB_CUDA(ctx, cudaMalloc((void **)&ctx->d_rgb, n * sizeof(double))); // room for the f64 resolve too
         ctx->accum_elems = n;
     }
     RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_accum, 0, n * sizeof(unsigned long long), ctx->stream));
@@ -335,9 +335,11 @@ int rrtb_render(rrtb_ctx *ctx, const rrtb_render_params *p, float *out_rgb, rrtb
     if (rc) return rc;
     cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
     RRTB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-    rc = launch_resolve(ctx, (const uint64_t *)ctx->d_accum, ctx->d_rgb, n);
+    rc = f64 ? launch_resolve_f64(ctx, (const uint64_t *)ctx->d_accum, (double *)ctx->d_rgb, n)
+             : launch_resolve(ctx, (const uint64_t *)ctx->d_accum, ctx->d_rgb, n);
     if (rc) return rc;
-    RRTB_CUDA(ctx, cudaMemcpyAsync(out_rgb, ctx->d_rgb, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaMemcpyAsync(out_rgb, ctx->d_rgb, n * (f64 ? sizeof(double) : sizeof(float)), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
     RRTB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
@@ -346,6 +348,16 @@ int rrtb_render(rrtb_ctx *ctx, const rrtb_render_params *p, float *out_rgb, rrtb
     local.kernel_launches += 1;
     if (stats) *stats = local;
     return RRTB_OK;
+}
+
+int rrtb_render(rrtb_ctx *ctx, const rrtb_render_params *p, float *out_rgb, rrtb_stats *stats)
+{
+    return render_host(ctx, p, out_rgb, stats, false);
+}
+
+int rrtb_render_f64(rrtb_ctx *ctx, const rrtb_render_params *p, double *out_rgb, rrtb_stats *stats)
+{
+    return render_host(ctx, p, out_rgb, stats, true);
 }
 
 int rrtb_probe_issue_rate(rrtb_ctx *ctx, double *ffma_lane_instr_per_s, double *mix_lane_instr_per_s)

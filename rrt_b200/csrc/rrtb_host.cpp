@@ -422,6 +422,25 @@ int rrtb_tonemap_rgb8(const float *rgb_sum, int width, int height, int spp, uint
     return RRTB_OK;
 }
 
+// color.h:8-23 with FP_T = double (the rrtd build): sqrt in double, clamp to [0, 0.999], * 256
+int rrtb_tonemap_rgb8_f64(const double *rgb_sum, int width, int height, int spp, uint8_t *rgb8)
+{
+    if (!rgb_sum || !rgb8 || width <= 0 || height <= 0 || spp <= 0) return RRTB_ERR_INVALID;
+    const double scale = 1.0 / spp;
+    for (int j = height - 1, k = 0; j >= 0; --j, ++k) {
+        for (int i = 0; i < width; ++i) {
+            const double *src = rgb_sum + 3 * ((size_t)j * width + i);
+            uint8_t *dst = rgb8 + 3 * ((size_t)k * width + i);
+            for (int c = 0; c < 3; ++c) {
+                double x = sqrt(scale * src[c]);
+                double cl = x < 0.0 ? 0.0 : (x > 0.999 ? 0.999 : x);
+                dst[c] = (uint8_t)(int)(256 * cl);
+            }
+        }
+    }
+    return RRTB_OK;
+}
+
 // Minimal PNG (8-bit RGB, zlib deflate, filter 0) -- stands where the reference calls stbi_write_png.
 static void png_chunk(FILE *f, const char *tag, const uint8_t *data, uint32_t len)
 {

@@ -73,6 +73,7 @@ DeviceScene device_scene(const rrtb_ctx *ctx);
 DeviceCamera device_camera(const rrtb_camera &c, int W, int H);
 int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum, rrtb_stats *stats);
 int launch_resolve(rrtb_ctx *ctx, const uint64_t *d_accum, float *d_out, size_t n);
+int launch_resolve_f64(rrtb_ctx *ctx, const uint64_t *d_accum, double *d_out, size_t n);
 int launch_accumulate(rrtb_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t n);
 int launch_trace(rrtb_ctx *ctx, const float *d_rays7, int n, float t_min, int mode, int32_t *d_id, float *d_t,
                  float *d_rec7);

@@ -185,6 +185,13 @@ __global__ void k_resolve(const unsigned long long *__restrict__ acc, float *__r
     for (; i < n; i += stride) out[i] = __double2float_rn((double)acc[i] * 9.094947017729282e-13); // 2^-40
 }
 
+__global__ void k_resolve_f64(const unsigned long long *__restrict__ acc, double *__restrict__ out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (double)acc[i] * 9.094947017729282e-13; // exact for sums below 2^53
+}
+
 __global__ void k_accumulate(unsigned long long *__restrict__ dst, const unsigned long long *__restrict__ src, size_t n)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -496,6 +503,16 @@ int launch_resolve(rrtb_ctx *ctx, const uint64_t *d_accum, float *d_out, size_t 
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
     if (blocks < 1) blocks = 1;
     k_resolve<<<blocks, 256, 0, ctx->stream>>>((const unsigned long long *)d_accum, d_out, n);
+    RRTB_CUDA(ctx, cudaGetLastError());
+    return RRTB_OK;
+}
+
+int launch_resolve_f64(rrtb_ctx *ctx, const uint64_t *d_accum, double *d_out, size_t n)
+{
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    k_resolve_f64<<<blocks, 256, 0, ctx->stream>>>((const unsigned long long *)d_accum, d_out, n);
     RRTB_CUDA(ctx, cudaGetLastError());
     return RRTB_OK;
 }

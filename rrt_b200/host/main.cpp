@@ -135,7 +135,7 @@ static int run_batch(const std::string &list, int w, int h, int spp, int depth, 
         }
         seconds += rrt.stats.seconds_render;
         rays += rrt.stats.rays;
-        rrtb_tonemap_rgb8(&fb[0].e[0], w, h, spp, rgb.data());
+        rrtb_tonemap_fp(&fb[0].e[0], w, h, spp, rgb.data());
         if (rrtb_write_png(png_file.c_str(), w, h, rgb.data()) != RRTB_OK) {
             std::cerr << "ERROR: could not write " << png_file << std::endl;
             return 1;
@@ -257,7 +257,7 @@ int main(int argc, char *argv[])
     gethostname(hostname, sizeof(hostname));
     // reference fields first (rrt.cu:312-315): date,host,CUDA<ver>,FP_T,W,H,spp,blocks,tx,ty,seconds ; then ours
     std::cerr << "stats," << std::put_time(&render_tm, "%c %Z,") << std::string(hostname) << ","
-              << "CUDA-rrtb" << rrtb_abi_version() << ",float," << image_width << "," << image_height << ","
+              << "CUDA-rrtb" << rrtb_abi_version() << "," RRTB_FP_NAME "," << image_width << "," << image_height << ","
               << num_samples << "," << rrt.stats.kernel_launches << "," << num_threads_x << "," << num_threads_y << ","
               << timer_seconds << "," << rrt.stats.rays << ","
               << (timer_seconds > 0 ? rrt.stats.rays / timer_seconds * 1e-6 : 0.0) << "," << rrt.stats.seconds_build
@@ -266,14 +266,14 @@ int main(int argc, char *argv[])
     if (png_filename == nullptr) {
         // PPM to stdout: rows top-down, one "r g b" line per pixel (main.cpp:140-149)
         std::vector<uint8_t> rgb((size_t)image_width * image_height * 3);
-        rrtb_tonemap_rgb8(&fb[0].e[0], image_width, image_height, num_samples, rgb.data());
+        rrtb_tonemap_fp(&fb[0].e[0], image_width, image_height, num_samples, rgb.data());
         std::cout << "P3\n" << image_width << ' ' << image_height << "\n255\n";
         for (size_t k = 0; k < rgb.size(); k += 3)
             std::cout << (int)rgb[k] << ' ' << (int)rgb[k + 1] << ' ' << (int)rgb[k + 2] << '\n';
     }
     else {
         std::vector<uint8_t> rgb((size_t)image_width * image_height * 3);
-        rrtb_tonemap_rgb8(&fb[0].e[0], image_width, image_height, num_samples, rgb.data());
+        rrtb_tonemap_fp(&fb[0].e[0], image_width, image_height, num_samples, rgb.data());
         if (rrtb_write_png(png_filename, image_width, image_height, rgb.data()) != RRTB_OK) {
             std::cerr << "ERROR: could not write " << png_filename << std::endl;
             std::exit(1);

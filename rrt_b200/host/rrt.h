@@ -11,12 +11,27 @@
 
 #include "rrtb.h"
 
-struct vec3 { // layout-compatible with the reference's float vec3 (vec3.h:21-81): 3 x FP_T
-    float e[3];
-    float x() const { return e[0]; }
-    float y() const { return e[1]; }
-    float z() const { return e[2]; }
+// FP_T as in the reference (rtweekend.h:20-28): `rrt` is built with -DUSE_FLOAT, `rrtd` without.  Here the
+// switch selects the framebuffer type (float or double sums); see rrtb_render / rrtb_render_f64.
+#ifdef USE_FLOAT
+typedef float FP_T;
+#define RRTB_FP_NAME "float"
+#else
+typedef double FP_T;
+#define RRTB_FP_NAME "double"
+#endif
+
+struct vec3 { // layout-compatible with the reference's vec3 (vec3.h:21-81): 3 x FP_T
+    FP_T e[3];
+    FP_T x() const { return e[0]; }
+    FP_T y() const { return e[1]; }
+    FP_T z() const { return e[2]; }
 };
+
+inline int rrtb_render_fp(rrtb_ctx *c, const rrtb_render_params *p, float *out, rrtb_stats *s) { return rrtb_render(c, p, out, s); }
+inline int rrtb_render_fp(rrtb_ctx *c, const rrtb_render_params *p, double *out, rrtb_stats *s) { return rrtb_render_f64(c, p, out, s); }
+inline int rrtb_tonemap_fp(const float *fb, int w, int h, int spp, uint8_t *rgb) { return rrtb_tonemap_rgb8(fb, w, h, spp, rgb); }
+inline int rrtb_tonemap_fp(const double *fb, int w, int h, int spp, uint8_t *rgb) { return rrtb_tonemap_rgb8_f64(fb, w, h, spp, rgb); }
 
 // Failure convention of the reference (rrt.cu:31-40): message on stderr, exit(99).
 inline void rrtb_check(int rc, rrtb_ctx *ctx, const char *what)
@@ -70,7 +85,7 @@ class Rrt {
         p.world = world;
         p.shard_mode = RRTB_SHARD_TILES;
         p.count_rays = 1;
-        rrtb_check(rrtb_render(ctx, &p, &fb[0].e[0], &stats), ctx, "rrtb_render");
+        rrtb_check(rrtb_render_fp(ctx, &p, &fb[0].e[0], &stats), ctx, "rrtb_render");
         return fb.data();
     }
 

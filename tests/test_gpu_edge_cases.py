@@ -181,3 +181,33 @@ def test_tree_top_staging_option_gives_the_same_image(ctx, monkeypatch):
     monkeypatch.delenv("RRTB_STAGE_TOP")
     d, _ = ctx.render(32, 24, 2, 50, seed=1)
     assert c.tobytes() == d.tobytes()
+
+
+def test_double_framebuffer_is_the_same_image(ctx, tmp_path, built_lib):
+    """rrtb_render_f64 (the `rrtd` framebuffer): double sums that round to exactly the float sums, and the
+    rrtd executable writes the same PNG as rrt (both tonemaps see the same exact accumulators)."""
+    import os
+    import subprocess
+
+    from PIL import Image
+
+    from conftest import ROOT, load_golden
+    from oracle_lib import ref_scene_path
+    from rrt_b200 import tonemap
+
+    scene, _ = load_golden("test2")
+    ctx.set_scene(scene)
+    f32, _ = ctx.render(80, 48, 5, 50, seed=4)
+    f64, _ = ctx.render(80, 48, 5, 50, seed=4, dtype=np.float64)
+    assert f64.dtype == np.float64 and np.array_equal(f64.astype(np.float32), f32)
+    assert np.abs(tonemap(f64, 5).astype(int) - tonemap(f32, 5).astype(int)).max() <= 1
+    p = ref_scene_path("test1.txt")
+    exe = os.path.join(ROOT, "rrt_b200", "bin")
+    if p and os.path.exists(os.path.join(exe, "rrtd")):
+        outs = []
+        for name in ("rrt", "rrtd"):
+            out = tmp_path / (name + ".png")
+            r = subprocess.run([os.path.join(exe, name), "-i", p, "-w", "90", "-h", "60", "-s", "4", "-o", str(out)], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0 and (",double," if name == "rrtd" else ",float,") in r.stderr
+            outs.append(np.asarray(Image.open(out)).astype(int))
+        assert np.abs(outs[0] - outs[1]).max() <= 1
