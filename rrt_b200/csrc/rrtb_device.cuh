@@ -21,6 +21,19 @@
 
 namespace rrtb {
 
+// -DRRTB_DEBUG_CHECKS builds librrtb200_dbg.so: invariants of the traversal stack and of the pool stacks are
+// counted into a device word that rrtb_render hands back in stats.reserved (compute-sanitizer is closed on
+// this GPU pool, so the bounds are checked by the code itself; tests/test_gpu_edge_cases.py).
+#ifdef RRTB_DEBUG_CHECKS
+__device__ unsigned int g_rrtb_violations;
+#define RRTB_CHECK(cond)                              \
+    do {                                              \
+        if (!(cond)) atomicAdd(&g_rrtb_violations, 1u); \
+    } while (0)
+#else
+#define RRTB_CHECK(cond) ((void)0)
+#endif
+
 // ---- scene as the kernels see it -----------------------------------------------------------------
 // Leaf record: 3 x float4 (48 B) per primitive, in LEAF ORDER (Morton order for the LBVH, object-id
 // order for the flat scan):
@@ -376,6 +389,7 @@ __device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, cons
     int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
     if (hl && hr) {
         bool left_first = tl <= tr;
+        RRTB_CHECK(sp >= 0 && sp < RRTB_STACK);
         stack[sp++] = left_first ? cr : cl;
         cur = left_first ? cl : cr;
     }

@@ -493,6 +493,11 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
             px = (unsigned long long)a.W * a.H;
         }
         stats->paths = px * (unsigned long long)a.n_local_samples;
+#ifdef RRTB_DEBUG_CHECKS
+        unsigned int viol = 0;
+        RRTB_CUDA(ctx, cudaMemcpyFromSymbol(&viol, g_rrtb_violations, sizeof(viol)));
+        stats->reserved = (int32_t)viol; // cumulative count of violated invariants (debug build only)
+#endif
     }
     return RRTB_OK;
 }

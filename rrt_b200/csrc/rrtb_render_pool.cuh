@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
             const int rank = __popc(idle_mask & lt_mask);
             if (slot < 0 && rank < take) {
                 slot = wp.tq[tq_n - 1 - rank];
+                RRTB_CHECK(slot >= 0 && slot < POOL && tq_n - 1 - rank >= 0);
                 ray.ox = wp.ox[slot]; ray.oy = wp.oy[slot]; ray.oz = wp.oz[slot];
                 ray.dx = wp.dx[slot]; ray.dy = wp.dy[slot]; ray.dz = wp.dz[slot];
                 ray.tm = wp.tm[slot];
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
             if (ended) wp.gq[gq_n + __popc(e_mask & lt_mask)] = (unsigned char)sl;
             tq_n += __popc(t_mask);
             gq_n += __popc(e_mask);
+            RRTB_CHECK(tq_n <= POOL && gq_n <= POOL && sq_n >= 0);
             __syncwarp(); // slot contents + stack entries visible to the lanes that will pop them
         }
         else if (gq_n >= 32 || (starving && gq_n > 0)) {
@@ -222,6 +224,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
                         wp.dx[sl] = r.dx; wp.dy[sl] = r.dy; wp.dz[sl] = r.dz;
                         wp.tm[sl] = r.tm;
                         wp.tr[sl] = 1.f; wp.tg[sl] = 1.f; wp.tb[sl] = 1.f;
+                        RRTB_CHECK(sl >= 0 && sl < POOL && j * a.W + i < a.W * a.H);
                         wp.pixel[sl] = j * a.W + i;
                         wp.sample[sl] = sample;
                         wp.bounce[sl] = 0;
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
             if (again) wp.gq[gq_n + __popc(g_mask & lt_mask)] = (unsigned char)sl;
             tq_n += __popc(t_mask);
             gq_n += __popc(g_mask);
+            RRTB_CHECK(tq_n <= POOL && gq_n <= POOL && tq_n + sq_n + gq_n <= POOL);
             __syncwarp();
         }
         else if (n_idle == 32) {
@@ -277,6 +281,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
                 }
                 sq_n += __popc(hit_mask);
                 gq_n += __popc(miss_mask);
+                RRTB_CHECK(sq_n <= POOL && gq_n <= POOL && tq_n + sq_n + gq_n <= POOL);
                 __syncwarp();
             }
         }

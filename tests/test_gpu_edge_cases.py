@@ -211,3 +211,50 @@ def test_double_framebuffer_is_the_same_image(ctx, tmp_path, built_lib):
             assert r.returncode == 0 and (",double," if name == "rrtd" else ",float,") in r.stderr
             outs.append(np.asarray(Image.open(out)).astype(int))
         assert np.abs(outs[0] - outs[1]).max() <= 1
+
+
+def test_debug_build_reports_no_invariant_violations(built_lib):
+    """compute-sanitizer is closed on this GPU pool, so the bounds of the traversal stack and of the pool's
+    slot stacks are checked by a -DRRTB_DEBUG_CHECKS build (librrtb200_dbg.so) that counts violated
+    invariants into stats.reserved.  Runs a mix of scenes, schedulers and shard modes in a subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    dbg = os.path.join(ROOT, "rrt_b200", "librrtb200_dbg.so")
+    if not os.path.exists(dbg):
+        pytest.skip("debug library not built (make -C rrt_b200/csrc dbg)")
+    code = r'''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import ctypes as C
+from conftest import load_golden
+from rrt_b200 import Context, Scene
+from rrt_b200.types import Stats
+from rrt_b200.synthetic import write_synthetic_scene
+ctx = Context(0)
+worst = 0
+def render(*a, **k):
+    global worst
+    p = ctx.params(*a, **k)
+    import numpy as np
+    out = np.empty((p.height, p.width, 3), np.float32)
+    st = Stats()
+    assert ctx.lib.rrtb_render(ctx.h, C.byref(p), C.c_void_p(out.ctypes.data), C.byref(st)) == 0
+    worst = max(worst, st.reserved)
+for name in ("final", "test2", "test3"):
+    scene, d = load_golden(name)
+    ctx.set_scene(scene, True)
+    for sched in (1, 2):
+        render(70, 45, 6, 50, 7, scheduler=sched, count_rays=True)
+    render(33, 17, 4, 50, 7, 1, 3, 1)
+write_synthetic_scene("/tmp/_dbg_synth.txt", n_spheres=1500, ico_level=2, grid=3)
+ctx.set_scene(Scene.from_file("/tmp/_dbg_synth.txt", 64, 36), True)
+render(64, 36, 4, 50, 3)
+print("violations", worst)
+''' % (ROOT, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, RRTB_LIB=dbg))
+    assert r.returncode == 0, r.stderr[-800:]
+    assert "violations 0" in r.stdout, r.stdout
