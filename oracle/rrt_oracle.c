@@ -258,6 +258,14 @@ static f3 triangle_normal(f3 v0, f3 v1, f3 v2)
     return unit3(cross3(unit3(sub3(v1, v0)), unit3(sub3(v2, v0))));
 }
 
+void orc_triangle_normal(const rrtb_triangle *tr, float n[3])
+{
+    f3 v = triangle_normal(ld3(tr->v0), ld3(tr->v1), ld3(tr->v2));
+    n[0] = v.x;
+    n[1] = v.y;
+    n[2] = v.z;
+}
+
 static int hit_t_only(const orc_scene *s, int id, f3 o, f3 d, float time, float t_min, float t_max, float *t)
 {
     objref r = obj_of(s, id);

@@ -85,6 +85,18 @@ void orc_radiance(const orc_scene *s, const orc_bvh *bvh, const float *ray7, int
 void orc_path(const orc_scene *s, const orc_bvh *bvh, int W, int H, int pixel, int sample, int max_depth,
               uint64_t seed, float *rgb, orc_counters *cnt);
 
+/* triangle.h:9-15: the float unit face normal the product stores in its leaf record */
+void orc_triangle_normal(const rrtb_triangle *tr, float n[3]);
+
+/* ---- the DOUBLE integrator (rrt_oracle_f64.c): FP_T = double semantics over the same float scene ---- */
+void orc_d_camera_ray(const rrtb_camera *cam, int W, int H, int pixel, int sample, uint64_t seed, double *ray7);
+/* closest hit, leaf tests in double; b may be NULL (flat scan). rec7 optional = p(3) n(3) front */
+void orc_d_trace(const orc_scene *s, const orc_bvh *b, const double *rays7, int n, double t_min, int32_t *id, double *t,
+                 double *rec7);
+void orc_d_scatter(const orc_scene *s, const double *in16, const uint32_t *rnd4, int n, double *out8);
+void orc_d_render(const orc_scene *s, const orc_bvh *bvh, int W, int H, int spp, int max_depth, uint64_t seed, double *out_rgb,
+                  uint64_t *out_fixed, orc_counters *cnt);
+
 /* color.h:8-23 */
 void orc_tonemap_rgb8(const float *rgb_sum, int W, int H, int spp, uint8_t *rgb8_topdown);
 

@@ -64,7 +64,7 @@ class Counters(C.Structure):
 
 def build_oracle():
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    src = [os.path.join(ORACLE_DIR, f) for f in ("rrt_oracle.c", "rrt_oracle.h")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("rrt_oracle.c", "rrt_oracle_f64.c", "rrt_oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
     return so
@@ -178,6 +178,42 @@ class Oracle:
         self.lib.orc_render(C.byref(self._s), self.bvh() if use_bvh else None, W, H, spp, max_depth, C.c_uint64(seed),
                             rank, world, shard_mode, C.c_void_p(out.ctypes.data), C.c_void_p(fixed.ctypes.data),
                             C.byref(cnt))
+        return out, fixed, cnt.as_dict()
+
+    # -- the double integrator (oracle/rrt_oracle_f64.c) --
+    def camera_rays_f64(self, W, H, pixels, sample, seed):
+        pixels = np.asarray(pixels, dtype=np.int32)
+        out = np.zeros((len(pixels), 7), np.float64)
+        f = self.lib.orc_d_camera_ray
+        for k, p in enumerate(pixels):
+            f(C.c_void_p(self.scene.camera.ctypes.data), W, H, int(p), int(sample), C.c_uint64(seed), C.c_void_p(out[k].ctypes.data))
+        return out
+
+    def trace_f64(self, rays7, t_min=0.001, mode="scan", want_rec=False):
+        rays7 = np.ascontiguousarray(rays7, dtype=np.float64)
+        n = len(rays7)
+        ids = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float64)
+        rec = np.zeros((n, 7), np.float64) if want_rec else None
+        self.lib.orc_d_trace(C.byref(self._s), self.bvh() if mode == "bvh" else None, C.c_void_p(rays7.ctypes.data), n,
+                             C.c_double(t_min), C.c_void_p(ids.ctypes.data), C.c_void_p(t.ctypes.data),
+                             C.c_void_p(rec.ctypes.data) if want_rec else None)
+        return (ids, t, rec) if want_rec else (ids, t)
+
+    def scatter_f64(self, in16, rnd4):
+        in16 = np.ascontiguousarray(in16, dtype=np.float64)
+        rnd4 = np.ascontiguousarray(rnd4, dtype=np.uint32)
+        out = np.zeros((len(in16), 8), np.float64)
+        self.lib.orc_d_scatter(C.byref(self._s), C.c_void_p(in16.ctypes.data), C.c_void_p(rnd4.ctypes.data), len(in16),
+                               C.c_void_p(out.ctypes.data))
+        return out
+
+    def render_f64(self, W, H, spp, max_depth=50, seed=1984, use_bvh=True):
+        out = np.zeros((H, W, 3), np.float64)
+        fixed = np.zeros((H, W, 3), np.uint64)
+        cnt = Counters()
+        self.lib.orc_d_render(C.byref(self._s), self.bvh() if use_bvh else None, W, H, spp, max_depth, C.c_uint64(seed),
+                              C.c_void_p(out.ctypes.data), C.c_void_p(fixed.ctypes.data), C.byref(cnt))
         return out, fixed, cnt.as_dict()
 
     def tonemap(self, rgb_sum, spp):
