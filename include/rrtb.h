@@ -118,6 +118,11 @@ enum { RRTB_SHARD_TILES = 0, RRTB_SHARD_SAMPLES = 1 };
  *   RRTB_SCHED_POOL    persistent threads, per-warp pool of paths in shared memory: lanes refill as soon as
  *                      their traversal ends, shading runs 32 wide (rrtb_render_pool.cuh) */
 enum { RRTB_SCHED_AUTO = 0, RRTB_SCHED_SIMPLE = 1, RRTB_SCHED_POOL = 2 };
+/* arithmetic of the integrator = the reference's two builds (rtweekend.h:20-28, Makefile:32-37):
+ *   RRTB_PRECISION_F32  `rrt`  (-DUSE_FLOAT): float rays / shading, intersection kernels exact to 2.2e-6 (default)
+ *   RRTB_PRECISION_F64  `rrtd` (FP_T = double): rays, hit points, normals, scattering and throughput in double;
+ *                       persistent one-path-per-lane kernel whatever `scheduler` says.  Same Philox streams. */
+enum { RRTB_PRECISION_F32 = 0, RRTB_PRECISION_F64 = 1 };
 
 typedef struct rrtb_render_params {
     int32_t width, height;     /* -w -h   (main.cpp:56-57) */
@@ -128,7 +133,7 @@ typedef struct rrtb_render_params {
     int32_t shard_mode;        /* RRTB_SHARD_TILES: interleaved 8x4-pixel tiles; RRTB_SHARD_SAMPLES: sample ranges */
     int32_t count_rays;        /* != 0: also count ray segments (stats.rays); same image either way */
     int32_t scheduler;         /* RRTB_SCHED_* */
-    int32_t reserved;
+    int32_t precision;         /* RRTB_PRECISION_* */
 } rrtb_render_params;
 
 typedef struct rrtb_stats {
@@ -176,10 +181,15 @@ int rrtb_probe_issue_rate(rrtb_ctx *ctx, double *ffma_lane_instr_per_s, double *
  * id[i] = object id or -1; t[i] = ray parameter; rec7 (optional, may be NULL) = p(3), normal(3), front. */
 int rrtb_trace_closest(rrtb_ctx *ctx, const float *rays7, int n, float t_min, int mode, int32_t *id, float *t,
                        float *rec7);
+/* The same for the double integrator (RRTB_PRECISION_F64): double rays in, double t / record out. */
+int rrtb_trace_closest_f64(rrtb_ctx *ctx, const double *rays7, int n, double t_min, int mode, int32_t *id, double *t,
+                           double *rec7);
 /* Primary rays exactly as the render kernel generates them (camera.h:31-38, rrt.cu:112-114) for
  * pixel indices pix[k] (= j*W+i) and sample index s. */
 int rrtb_camera_rays(rrtb_ctx *ctx, const rrtb_render_params *p, const int32_t *pix, int n, int sample,
                      float *rays7);
+int rrtb_camera_rays_f64(rrtb_ctx *ctx, const rrtb_render_params *p, const int32_t *pix, int n, int sample,
+                         double *rays7);
 /* LBVH introspection (all HOST pointers, any may be NULL):
  *   morton[n]            30-bit code of primitive i (object-id order)
  *   perm[n]              sorted position k -> object id
@@ -197,6 +207,7 @@ int rrtb_philox(rrtb_ctx *ctx, const uint32_t *ctr4, int n, uint32_t key0, uint3
  * rnd4 per item : the Philox block (4 x uint32) the kernel would have drawn for this bounce
  * out8 per item : scattered direction(3), attenuation(3), scattered(0/1), unused                  */
 int rrtb_scatter(rrtb_ctx *ctx, const float *in16, const uint32_t *rnd4, int n, float *out8);
+int rrtb_scatter_f64(rrtb_ctx *ctx, const double *in16, const uint32_t *rnd4, int n, double *out8);
 
 /* ---- host side of the drop-in (C++ inside the same library; no GPU needed) -------------------
  * Scene-file parser with the reference grammar and quirks (scene.h:212-452). */

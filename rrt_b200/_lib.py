@@ -15,8 +15,8 @@ LIB_PATH = os.environ.get("RRTB_LIB") or os.path.join(_HERE, "librrtb200.so")  #
 SYMBOLS = [
     "rrtb_abi_version", "rrtb_create", "rrtb_destroy", "rrtb_last_error", "rrtb_device_info",
     "rrtb_scene_set", "rrtb_camera_set", "rrtb_render", "rrtb_render_f64", "rrtb_render_device", "rrtb_resolve_device",
-    "rrtb_accumulate_device", "rrtb_trace_closest", "rrtb_camera_rays", "rrtb_bvh_size", "rrtb_bvh_download",
-    "rrtb_philox", "rrtb_scatter", "rrtb_probe_issue_rate", "rrtb_scene_parse_file", "rrtb_scene_free", "rrtb_scene_counts",
+    "rrtb_accumulate_device", "rrtb_trace_closest", "rrtb_trace_closest_f64", "rrtb_camera_rays", "rrtb_camera_rays_f64",
+    "rrtb_bvh_size", "rrtb_bvh_download", "rrtb_philox", "rrtb_scatter", "rrtb_scatter_f64", "rrtb_probe_issue_rate", "rrtb_scene_parse_file", "rrtb_scene_free", "rrtb_scene_counts",
     "rrtb_scene_camera", "rrtb_scene_materials", "rrtb_scene_spheres", "rrtb_scene_mspheres",
     "rrtb_scene_triangles", "rrtb_scene_upload", "rrtb_camera_derive", "rrtb_tonemap_rgb8", "rrtb_tonemap_rgb8_f64", "rrtb_write_png",
 ]
@@ -61,6 +61,9 @@ def load():
         "rrtb_accumulate_device": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "rrtb_trace_closest": (C.c_int, [vp, vp, C.c_int, f32, C.c_int, vp, vp, vp]),
         "rrtb_camera_rays": (C.c_int, [vp, P(RenderParams), vp, C.c_int, C.c_int, vp]),
+        "rrtb_trace_closest_f64": (C.c_int, [vp, vp, C.c_int, C.c_double, C.c_int, vp, vp, vp]),
+        "rrtb_camera_rays_f64": (C.c_int, [vp, P(RenderParams), vp, C.c_int, C.c_int, vp]),
+        "rrtb_scatter_f64": (C.c_int, [vp, vp, vp, C.c_int, vp]),
         "rrtb_bvh_size": (C.c_int, [vp, P(i32)]),
         "rrtb_bvh_download": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
         "rrtb_philox": (C.c_int, [vp, vp, C.c_int, u32, u32, vp]),

@@ -103,6 +103,9 @@ class Scene:
         return "\n".join(lines)
 
 
+_PRECISION = {"f32": 0, "f64": 1, 0: 0, 1: 1}
+
+
 class Context:
     """One GPU.  Raises RrtbError(RRTB_ERR_NO_DEVICE) when there is no CUDA device: no CPU fallback."""
 
@@ -165,15 +168,17 @@ class Context:
 
     # -- render -----------------------------------------------------------------------------------------
     @staticmethod
-    def params(width, height, spp, max_depth=50, seed=1984, rank=0, world=1, shard_mode=0, count_rays=False, scheduler=0):
+    def params(width, height, spp, max_depth=50, seed=1984, rank=0, world=1, shard_mode=0, count_rays=False, scheduler=0,
+               precision="f32"):
         return RenderParams(int(width), int(height), int(spp), int(max_depth), int(seed), int(rank), int(world),
-                            int(shard_mode), 1 if count_rays else 0, int(scheduler), 0)
+                            int(shard_mode), 1 if count_rays else 0, int(scheduler), _PRECISION[precision])
 
     def render(self, width, height, spp, max_depth=50, seed=1984, rank=0, world=1, shard_mode=0, count_rays=False, out=None, scheduler=0,
-               dtype=np.float32):
+               dtype=np.float32, precision="f32"):
         """Host-buffer path (what Rrt::render returns): [H, W, 3] SUMS, row 0 = bottom scanline.
-        dtype float32 = the `rrt` framebuffer, float64 = the `rrtd` framebuffer (rrtb_render_f64)."""
-        p = self.params(width, height, spp, max_depth, seed, rank, world, shard_mode, count_rays, scheduler)
+        dtype float32 = the `rrt` framebuffer, float64 = the `rrtd` framebuffer (rrtb_render_f64);
+        precision "f32" / "f64" = the arithmetic of the integrator (the reference's rrt / rrtd builds)."""
+        p = self.params(width, height, spp, max_depth, seed, rank, world, shard_mode, count_rays, scheduler, precision)
         dtype = np.dtype(dtype) if out is None else out.dtype
         assert dtype in (np.dtype(np.float32), np.dtype(np.float64))
         if out is None:
@@ -212,6 +217,30 @@ class Context:
         out = np.zeros((len(pixels), 7), np.float32)
         p = self.params(width, height, 1, 1, seed)
         self._check(self.lib.rrtb_camera_rays(self.h, C.byref(p), _vp(pixels), len(pixels), int(sample), _vp(out)))
+        return out
+
+    def trace_f64(self, rays7, t_min=0.001, mode="bvh", want_rec=False):
+        rays7 = np.ascontiguousarray(rays7, dtype=np.float64).reshape(-1, 7)
+        n = len(rays7)
+        ids = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float64)
+        rec = np.zeros((n, 7), np.float64) if want_rec else None
+        self._check(self.lib.rrtb_trace_closest_f64(self.h, _vp(rays7), n, C.c_double(t_min), 1 if mode == "bvh" else 0, _vp(ids),
+                                                    _vp(t), _vp(rec) if want_rec else C.c_void_p(0)))
+        return (ids, t, rec) if want_rec else (ids, t)
+
+    def camera_rays_f64(self, width, height, pixels, sample, seed=1984):
+        pixels = np.ascontiguousarray(pixels, dtype=np.int32)
+        out = np.zeros((len(pixels), 7), np.float64)
+        p = self.params(width, height, 1, 1, seed)
+        self._check(self.lib.rrtb_camera_rays_f64(self.h, C.byref(p), _vp(pixels), len(pixels), int(sample), _vp(out)))
+        return out
+
+    def scatter_f64(self, in16, rnd4):
+        in16 = np.ascontiguousarray(in16, dtype=np.float64).reshape(-1, 16)
+        rnd4 = np.ascontiguousarray(rnd4, dtype=np.uint32).reshape(-1, 4)
+        out = np.zeros((len(in16), 8), np.float64)
+        self._check(self.lib.rrtb_scatter_f64(self.h, _vp(in16), _vp(rnd4), len(in16), _vp(out)))
         return out
 
     def bvh_arrays(self):
@@ -282,7 +311,9 @@ class Rrt:
     threads_x/threads_y are accepted for drop-in compatibility and ignored: the persistent kernel picks
     its own launch shape (the reference's `-tx/-ty` tuned a one-thread-per-pixel grid, rrt.cu:192-193)."""
 
-    def __init__(self, image_width, image_height, samples_per_pixel, max_depth, use_bvh=True, threads_x=8, threads_y=8, device=0, seed=1984):
+    def __init__(self, image_width, image_height, samples_per_pixel, max_depth, use_bvh=True, threads_x=8, threads_y=8, device=0, seed=1984,
+                 precision="f32"):
+        self.precision = precision  # "f32" = the reference's rrt build, "f64" = rrtd (FP_T = double)
         self.image_width = image_width
         self.image_height = image_height
         self.samples_per_pixel = samples_per_pixel
@@ -295,8 +326,10 @@ class Rrt:
         self.stats = None
 
     def render(self, the_scene):
-        """-> fb: float32 [H, W, 3]; fb[j, i] is the SUM over samples for pixel (i, j), j = 0 bottom row
-        (the reference returns vec3* indexed j*W+i, rrt.cu:121,334)."""
+        """-> fb: FP_T [H, W, 3] (float32, or float64 for precision "f64"); fb[j, i] is the SUM over samples for
+        pixel (i, j), j = 0 bottom row (the reference returns vec3* indexed j*W+i, rrt.cu:121,334)."""
         self.ctx.set_scene(the_scene, self.bvh)
-        self.fb, self.stats = self.ctx.render(self.image_width, self.image_height, self.samples_per_pixel, self.max_depth, self.seed, count_rays=True)
+        f64 = _PRECISION[self.precision] == 1
+        self.fb, self.stats = self.ctx.render(self.image_width, self.image_height, self.samples_per_pixel, self.max_depth, self.seed,
+                                              count_rays=True, dtype=np.float64 if f64 else np.float32, precision=self.precision)
         return self.fb

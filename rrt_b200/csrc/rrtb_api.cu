@@ -279,6 +279,7 @@ static int check_render(rrtb_ctx *ctx, const rrtb_render_params *p)
     if ((long long)p->width * p->height >= (1ll << 28)) return invalid(ctx, "image too large (limit 2^28 pixels)");
     if (p->world > 1 && (p->rank < 0 || p->rank >= p->world)) return invalid(ctx, "rank out of range");
     if (p->shard_mode != RRTB_SHARD_TILES && p->shard_mode != RRTB_SHARD_SAMPLES) return invalid(ctx, "bad shard_mode");
+    if (p->precision != RRTB_PRECISION_F32 && p->precision != RRTB_PRECISION_F64) return invalid(ctx, "bad precision");
     return RRTB_OK;
 }
 
@@ -492,6 +493,75 @@ int rrtb_scatter(rrtb_ctx *ctx, const float *in16, const uint32_t *rnd4, int n, 
     int rc = launch_scatter(ctx, (const float *)di.p, (const uint32_t *)dr.p, n, (float *)dout.p);
     if (rc) return rc;
     RRTB_CUDA(ctx, cudaMemcpyAsync(out8, dout.p, 32 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RRTB_OK;
+}
+
+// ---- hooks of the double integrator ----------------------------------------------------------------------
+int rrtb_trace_closest_f64(rrtb_ctx *ctx, const double *rays7, int n, double t_min, int mode, int32_t *id, double *t,
+                           double *rec7)
+{
+    if (!ctx || !rays7 || !id || !t || n < 0) return RRTB_ERR_INVALID;
+    if (!ctx->has_scene) {
+        ctx->err = "trace before rrtb_scene_set";
+        return RRTB_ERR_NO_SCENE;
+    }
+    if (n == 0) return RRTB_OK;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dr, di, dt, drec;
+    HOOK_ALLOC(dr, sizeof(double) * 7 * (size_t)n);
+    HOOK_ALLOC(di, sizeof(int) * (size_t)n);
+    HOOK_ALLOC(dt, sizeof(double) * (size_t)n);
+    if (rec7) HOOK_ALLOC(drec, sizeof(double) * 7 * (size_t)n);
+    RRTB_CUDA(ctx, cudaMemcpyAsync(dr.p, rays7, sizeof(double) * 7 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_trace_f64(ctx, (const double *)dr.p, n, t_min, mode ? 1 : 0, (int32_t *)di.p, (double *)dt.p,
+                              rec7 ? (double *)drec.p : nullptr);
+    if (rc) return rc;
+    RRTB_CUDA(ctx, cudaMemcpyAsync(id, di.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaMemcpyAsync(t, dt.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rec7) RRTB_CUDA(ctx, cudaMemcpyAsync(rec7, drec.p, sizeof(double) * 7 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RRTB_OK;
+}
+
+int rrtb_camera_rays_f64(rrtb_ctx *ctx, const rrtb_render_params *p, const int32_t *pix, int n, int sample, double *rays7)
+{
+    if (!ctx || !p || !pix || !rays7 || n < 0) return RRTB_ERR_INVALID;
+    if (!ctx->has_scene) {
+        ctx->err = "camera rays before rrtb_scene_set";
+        return RRTB_ERR_NO_SCENE;
+    }
+    if (n == 0) return RRTB_OK;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf dp, dr;
+    HOOK_ALLOC(dp, sizeof(int) * (size_t)n);
+    HOOK_ALLOC(dr, sizeof(double) * 7 * (size_t)n);
+    RRTB_CUDA(ctx, cudaMemcpyAsync(dp.p, pix, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_camera_rays_f64(ctx, p, (const int32_t *)dp.p, n, sample, (double *)dr.p);
+    if (rc) return rc;
+    RRTB_CUDA(ctx, cudaMemcpyAsync(rays7, dr.p, sizeof(double) * 7 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RRTB_OK;
+}
+
+int rrtb_scatter_f64(rrtb_ctx *ctx, const double *in16, const uint32_t *rnd4, int n, double *out8)
+{
+    if (!ctx || !in16 || !rnd4 || !out8 || n < 0) return RRTB_ERR_INVALID;
+    if (!ctx->has_scene) {
+        ctx->err = "scatter before rrtb_scene_set";
+        return RRTB_ERR_NO_SCENE;
+    }
+    if (n == 0) return RRTB_OK;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf di, dr, dout;
+    HOOK_ALLOC(di, 128 * (size_t)n);
+    HOOK_ALLOC(dr, 16 * (size_t)n);
+    HOOK_ALLOC(dout, 64 * (size_t)n);
+    RRTB_CUDA(ctx, cudaMemcpyAsync(di.p, in16, 128 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    RRTB_CUDA(ctx, cudaMemcpyAsync(dr.p, rnd4, 16 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_scatter_f64(ctx, (const double *)di.p, (const uint32_t *)dr.p, n, (double *)dout.p);
+    if (rc) return rc;
+    RRTB_CUDA(ctx, cudaMemcpyAsync(out8, dout.p, 64 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RRTB_OK;
 }

@@ -82,5 +82,11 @@ int launch_camera_rays(rrtb_ctx *ctx, const rrtb_render_params *p, const int32_t
 int launch_philox(rrtb_ctx *ctx, const uint32_t *d_ctr, int n, uint32_t k0, uint32_t k1, uint32_t *d_out);
 int launch_probe(rrtb_ctx *ctx, int mix, double *lane_instr_per_s);
 int launch_scatter(rrtb_ctx *ctx, const float *d_in16, const uint32_t *d_rnd4, int n, float *d_out8);
+// the double integrator's hooks (rrtb_render_f64.cuh)
+int launch_trace_f64(rrtb_ctx *ctx, const double *d_rays7, int n, double t_min, int mode, int32_t *d_id, double *d_t,
+                     double *d_rec7);
+int launch_camera_rays_f64(rrtb_ctx *ctx, const rrtb_render_params *p, const int32_t *d_pix, int n, int sample,
+                           double *d_rays7);
+int launch_scatter_f64(rrtb_ctx *ctx, const double *d_in16, const uint32_t *d_rnd4, int n, double *d_out8);
 
 } // namespace rrtb

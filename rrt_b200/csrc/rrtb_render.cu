@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 2) k_render(const RenderArgs a)
 
 } // namespace rrtb
 #include "rrtb_render_pool.cuh"
+#include "rrtb_render_f64.cuh"
 namespace rrtb {
 
 __global__ void k_resolve(const unsigned long long *__restrict__ acc, float *__restrict__ out, size_t n)
@@ -422,7 +423,8 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     if (a.n_local_samples < 0) a.n_local_samples = 0;
     a.n_chunks = (a.n_local_samples + CHUNK - 1) / CHUNK;
     a.n_items = (unsigned long long)a.n_local_tiles * (unsigned long long)a.n_chunks * 32ull;
-    const bool use_pool = ctx->use_bvh != 0 && p->scheduler != RRTB_SCHED_SIMPLE;
+    const bool f64 = p->precision == RRTB_PRECISION_F64;
+    const bool use_pool = ctx->use_bvh != 0 && p->scheduler != RRTB_SCHED_SIMPLE && !f64;
     if (use_pool) // the pool scheduler hands out single camera paths: (tile, sample, pixel in tile)
         a.n_items = (unsigned long long)a.n_local_tiles * (unsigned long long)a.n_local_samples * 32ull;
     a.accum = (unsigned long long *)d_accum;
@@ -445,7 +447,13 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     if (a.n_items > 0 && a.max_depth > 0) { // max_depth 0: the bounce loop never runs (rrt.cu:47), the image is black
         const bool bvh = ctx->use_bvh != 0, cnt = p->count_rays != 0;
         int rc;
-        if (bvh && p->scheduler != RRTB_SCHED_SIMPLE) {
+        if (f64) {
+            if (bvh && cnt) rc = launch_persistent(ctx, k_render_f64<true, true>, a, &blocks);
+            else if (bvh) rc = launch_persistent(ctx, k_render_f64<true, false>, a, &blocks);
+            else if (cnt) rc = launch_persistent(ctx, k_render_f64<false, true>, a, &blocks);
+            else rc = launch_persistent(ctx, k_render_f64<false, false>, a, &blocks);
+        }
+        else if (use_pool) {
             bool stage_top = false; // option, see rrtb_render_pool.cuh
             if (const char *e = getenv("RRTB_STAGE_TOP")) stage_top = atoi(e) != 0;
             if (cnt) rc = launch_pool(ctx, k_render_pool<true, 2, false>, a, &blocks, false);
@@ -564,6 +572,34 @@ int launch_scatter(rrtb_ctx *ctx, const float *d_in16, const uint32_t *d_rnd4, i
 {
     if (n <= 0) return RRTB_OK;
     k_scatter_test<<<(n + 127) / 128, 128, 0, ctx->stream>>>(device_scene(ctx), d_in16, d_rnd4, n, d_out8);
+    RRTB_CUDA(ctx, cudaGetLastError());
+    return RRTB_OK;
+}
+
+int launch_trace_f64(rrtb_ctx *ctx, const double *d_rays7, int n, double t_min, int mode, int32_t *d_id, double *d_t,
+                     double *d_rec7)
+{
+    if (n <= 0) return RRTB_OK;
+    k_trace_f64<<<(n + 127) / 128, 128, 0, ctx->stream>>>(device_scene(ctx), d_rays7, n, t_min, mode, d_id, d_t, d_rec7);
+    RRTB_CUDA(ctx, cudaGetLastError());
+    return RRTB_OK;
+}
+
+int launch_camera_rays_f64(rrtb_ctx *ctx, const rrtb_render_params *p, const int32_t *d_pix, int n, int sample,
+                           double *d_rays7)
+{
+    if (n <= 0) return RRTB_OK;
+    uint2 key = make_uint2((uint32_t)p->seed, (uint32_t)(p->seed >> 32));
+    k_camera_rays_f64<<<(n + 127) / 128, 128, 0, ctx->stream>>>(device_camera(ctx->cam, p->width, p->height), p->width, p->height,
+                                                                 key, d_pix, n, sample, d_rays7);
+    RRTB_CUDA(ctx, cudaGetLastError());
+    return RRTB_OK;
+}
+
+int launch_scatter_f64(rrtb_ctx *ctx, const double *d_in16, const uint32_t *d_rnd4, int n, double *d_out8)
+{
+    if (n <= 0) return RRTB_OK;
+    k_scatter_test_f64<<<(n + 127) / 128, 128, 0, ctx->stream>>>(device_scene(ctx), d_in16, d_rnd4, n, d_out8);
     RRTB_CUDA(ctx, cudaGetLastError());
     return RRTB_OK;
 }

@@ -12,13 +12,16 @@
 #include "rrtb.h"
 
 // FP_T as in the reference (rtweekend.h:20-28): `rrt` is built with -DUSE_FLOAT, `rrtd` without.  Here the
-// switch selects the framebuffer type (float or double sums); see rrtb_render / rrtb_render_f64.
+// switch selects the integrator's arithmetic (RRTB_PRECISION_*) and the framebuffer type (float or double sums;
+// rrtb_render / rrtb_render_f64).
 #ifdef USE_FLOAT
 typedef float FP_T;
 #define RRTB_FP_NAME "float"
+#define RRTB_FP_PRECISION RRTB_PRECISION_F32
 #else
 typedef double FP_T;
 #define RRTB_FP_NAME "double"
+#define RRTB_FP_PRECISION RRTB_PRECISION_F64
 #endif
 
 struct vec3 { // layout-compatible with the reference's vec3 (vec3.h:21-81): 3 x FP_T
@@ -85,6 +88,7 @@ class Rrt {
         p.world = world;
         p.shard_mode = RRTB_SHARD_TILES;
         p.count_rays = 1;
+        p.precision = RRTB_FP_PRECISION;
         rrtb_check(rrtb_render_fp(ctx, &p, &fb[0].e[0], &stats), ctx, "rrtb_render");
         return fb.data();
     }

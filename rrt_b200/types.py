@@ -53,7 +53,7 @@ class RenderParams(C.Structure):
         ("shard_mode", C.c_int32),
         ("count_rays", C.c_int32),
         ("scheduler", C.c_int32),
-        ("reserved", C.c_int32),
+        ("precision", C.c_int32),
     ]
 
 
