@@ -364,6 +364,7 @@ def main():
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--shard", default="tiles", choices=["tiles", "samples"])
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"], help="f64 = the double integrator (the reference's rrtd build); not the headline")
     args = ap.parse_args()
 
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
@@ -411,7 +412,9 @@ def main():
     acc = torch.zeros(n, dtype=torch.int64, device=dev)
     out = torch.empty(n, dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-    params = ctx.params(Wl, Hl, spp, DEPTH, SEED, rank, world, shard_mode, False)
+    f64 = args.precision == "f64"
+    headline = headline and not f64
+    params = ctx.params(Wl, Hl, spp, DEPTH, SEED, rank, world, shard_mode, False, precision=args.precision)
 
     def barrier():
         if world > 1:
@@ -433,7 +436,7 @@ def main():
             ctx.resolve_device(acc.data_ptr(), out.data_ptr(), n)
 
     # counting pass (untimed): rays and per-ray work of exactly this workload and shard
-    pc = ctx.params(Wl, Hl, spp, DEPTH, SEED, rank, world, shard_mode, True)
+    pc = ctx.params(Wl, Hl, spp, DEPTH, SEED, rank, world, shard_mode, True, precision=args.precision)
     acc.zero_()
     torch.cuda.synchronize()
     cst = ctx.render_device(pc, acc.data_ptr())
@@ -470,14 +473,14 @@ def main():
     value = total_rays / sec_per_step / 1e6
 
     # ---- e2e: through the C ABI with host buffers, every step: scene upload + LBVH build + render + D2H
-    host_out = np.empty((Hl, Wl, 3), np.float32)
+    host_out = np.empty((Hl, Wl, 3), np.float64 if f64 else np.float32)
     h2d = scene.camera.nbytes + scene.materials.nbytes + scene.spheres.nbytes + scene.mspheres.nbytes + scene.triangles.nbytes
     d2h = host_out.nbytes if rank == 0 else 0
 
     def e2e_step():
         ctx.set_scene(scene, use_bvh=True)
         if world == 1:
-            ctx.render(Wl, Hl, spp, DEPTH, SEED, out=host_out)
+            ctx.render(Wl, Hl, spp, DEPTH, SEED, out=host_out, precision=args.precision)
         else:
             acc.zero_()
             torch.cuda.synchronize()
@@ -513,9 +516,10 @@ def main():
         except Exception:
             pass
         line = {
-            "metric": METRIC if args.workload == "final" else "Mrays/s on %s" % wl["label"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": (METRIC if args.workload == "final" else "Mrays/s on %s" % wl["label"]) + (" [double integrator, rrtd semantics]" if f64 else ""), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 (f64 leaf discriminants, u64 fixed-point accumulation)", "data": "%s (%s)" % (wl["data"], scene_src),
+            "dtype": "f64 (float slab tests, u64 fixed-point accumulation)" if f64 else "f32 (f64 leaf discriminants, u64 fixed-point accumulation)",
+            "data": "%s (%s)" % (wl["data"], scene_src),
             "config": {"workload": "%s %dx%d, %d spp, depth 50 (%s)" % (wl["label"], Wl, Hl, spp, wl["config"]), "prims": scene.n_objects,
                        "sharding": "one image, %s over %d GPU(s), NCCL reduce of u64 accumulators" % ("interleaved 8x4 tiles" if shard_mode == 0 else "interleaved samples", world),
                        "l2": "256 MiB flush written between timed iterations", "rays_per_step": total_rays,
@@ -523,7 +527,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "rrtb_scene_set (upload + LBVH build) + rrtb_render (render + resolve + D2H) per step"},
             "gpu_launches": args.steps * 2,
-            "kernel": {"name": "rrtb::k_render_pool<false>", "avg_ms": kern_s * 1e3, "share_of_step": kern_s / sec_per_step},
+            "kernel": {"name": "rrtb::k_render_f64<true,false>" if f64 else "rrtb::k_render_pool<false>", "avg_ms": kern_s * 1e3, "share_of_step": kern_s / sec_per_step},
             "roofline": {"bound": "fp32_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T lane-instr/s",
                          "frac": achieved / peak, "traffic": traffic, "w_ray": wr,
                          "peak_source": "measured on this device by rrtb_probe_issue_rate: FFMA-only loop %.2f T lane-instr/s (an FFMA+FMNMX "
@@ -533,7 +537,9 @@ def main():
             "clocks": clocks,
             "wall_s": wall,
         }
-        if world == 1 and not args.no_baselines and args.workload == "final":
+        if f64:
+            line["roofline"]["note"] = "W_ray counts the float integrator's instructions; reported for throughput only in the f64 build"
+        if world == 1 and not args.no_baselines and args.workload == "final" and not f64:
             line["cpu_baseline"] = cpu_baseline_sample(total_rays / tot["paths"])
             g = reference_gpu_baseline()
             if g:
