@@ -184,8 +184,9 @@ def test_tree_top_staging_option_gives_the_same_image(ctx, monkeypatch):
 
 
 def test_double_framebuffer_is_the_same_image(ctx, tmp_path, built_lib):
-    """rrtb_render_f64 (the `rrtd` framebuffer): double sums that round to exactly the float sums, and the
-    rrtd executable writes the same PNG as rrt (both tonemaps see the same exact accumulators)."""
+    """rrtb_render_f64 (the `rrtd` framebuffer) over the FLOAT integrator: double sums that round to exactly the
+    float sums.  The rrtd executable additionally switches the integrator to double (tests/test_gpu_f64.py): same
+    Philox streams, so its PNG equals rrt's except where a rounding difference sent a path elsewhere."""
     import os
     import subprocess
 
@@ -210,7 +211,7 @@ def test_double_framebuffer_is_the_same_image(ctx, tmp_path, built_lib):
             r = subprocess.run([os.path.join(exe, name), "-i", p, "-w", "90", "-h", "60", "-s", "4", "-o", str(out)], capture_output=True, text=True, timeout=300)
             assert r.returncode == 0 and (",double," if name == "rrtd" else ",float,") in r.stderr
             outs.append(np.asarray(Image.open(out)).astype(int))
-        assert np.abs(outs[0] - outs[1]).max() <= 1
+        assert (np.abs(outs[0] - outs[1]).max(axis=2) <= 1).mean() > 0.97
 
 
 def test_debug_build_reports_no_invariant_violations(built_lib):
