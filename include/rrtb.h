@@ -78,6 +78,20 @@ typedef struct rrtb_triangle { /* world-space, already instanced (scene.h:157-17
     int32_t material;
 } rrtb_triangle;
 
+/* SURVEY 8f4 -- "motion blur for object instances" (the reference's README.md:62 to-do; it has no such
+ * primitive, the model below follows its moving_sphere.h:27-30): a triangle of an instance that TRANSLATES
+ * linearly by `delta` between time0 and time1.  Vertices are given at time0.  The library works on
+ *   rate[k] = delta[k] / (time1 - time0),  base[k] = fma(-rate[k], time0, v0[k])      (float)
+ *   v0(time) = fma(rate, time, base);  v1(time) = v0(time) + (v1 - v0);  v2(time) = v0(time) + (v2 - v0)
+ * Its box spans the camera's shutter interval, as a moving sphere's does (rrt.cu:169).  Object ids of moving
+ * triangles follow the static triangles'. */
+typedef struct rrtb_mtriangle {
+    float v0[3], v1[3], v2[3];
+    float delta[3];
+    float time0, time1;
+    int32_t material;
+} rrtb_mtriangle;
+
 /* ---- context ------------------------------------------------------------------------------- */
 
 typedef struct rrtb_ctx rrtb_ctx;
@@ -104,6 +118,9 @@ int rrtb_device_info(rrtb_ctx *ctx, int64_t *out4, char *name, int name_len);
 int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *materials, int n_materials,
                    const rrtb_sphere *spheres, int n_spheres, const rrtb_msphere *mspheres, int n_mspheres,
                    const rrtb_triangle *triangles, int n_triangles, int use_bvh);
+/* Stage moving triangles for the NEXT rrtb_scene_set / rrtb_scene_upload on this context, which
+ * consumes them (a later rrtb_scene_set without a new staging call has none).  n == 0 clears the stage. */
+int rrtb_scene_stage_moving_triangles(rrtb_ctx *ctx, const rrtb_mtriangle *mtriangles, int n_mtriangles);
 /* Replace only the camera (animation frames that differ in the camera only). */
 int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam);
 
@@ -214,7 +231,11 @@ int rrtb_scatter_f64(rrtb_ctx *ctx, const double *in16, const uint32_t *rnd4, in
 
 typedef struct rrtb_scene rrtb_scene;
 
-/* On failure *out = NULL and *ref_exit_code (optional) receives the exit code the reference would
+/* One grammar EXTENSION (a line the reference ignores silently, like any unknown prefix):
+ *   mobj <obj index> <material> <dx> <dy> <dz> <time0> <time1> [t x y z | s x y z | r deg x y z]...
+ * = `obj` (scene.h:387-427) whose instance, placed by the transforms at time0, translates by (dx, dy, dz) until
+ * time1 -- the instance counterpart of `msphere c0 c1 time0 time1 r material`.
+ * On failure *out = NULL and *ref_exit_code (optional) receives the exit code the reference would
  * have used (1, 2, 3 or 4); err/err_len (optional) receive the reference's message. */
 int rrtb_scene_parse_file(const char *path, int image_width, int image_height, rrtb_scene **out,
                           int *ref_exit_code, char *err, int err_len);
@@ -226,6 +247,9 @@ const rrtb_material *rrtb_scene_materials(const rrtb_scene *s);
 const rrtb_sphere *rrtb_scene_spheres(const rrtb_scene *s);
 const rrtb_msphere *rrtb_scene_mspheres(const rrtb_scene *s);
 const rrtb_triangle *rrtb_scene_triangles(const rrtb_scene *s);
+/* moving triangles of `mobj` instances (grammar extension, see rrtb_scene_parse_file) */
+int rrtb_scene_mtriangle_count(const rrtb_scene *s);
+const rrtb_mtriangle *rrtb_scene_mtriangles(const rrtb_scene *s);
 /* rrtb_scene_set with a parsed scene. */
 int rrtb_scene_upload(rrtb_ctx *ctx, const rrtb_scene *s, int use_bvh);
 /* camera.h:8-29 in the reference's float arithmetic. */

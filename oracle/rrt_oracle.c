@@ -174,14 +174,15 @@ void orc_camera_ray(const rrtb_camera *cam, int W, int H, int pixel, int sample,
  * sphere quadratic (oc, half_b, c, discriminant) is evaluated in double from the float inputs;
  * the roots are then formed in float with the cancellation-free pair q/a, c/q.
  * ---------------------------------------------------------------------------------------------- */
-typedef struct { int type; /* 0 sphere 1 msphere 2 triangle */ int idx; } objref;
+typedef struct { int type; /* 0 sphere 1 msphere 2 triangle 3 moving triangle */ int idx; } objref;
 
 static inline objref obj_of(const orc_scene *s, int id)
 {
     objref r;
     if (id < s->n_spheres) { r.type = 0; r.idx = id; }
     else if (id < s->n_spheres + s->n_mspheres) { r.type = 1; r.idx = id - s->n_spheres; }
-    else { r.type = 2; r.idx = id - s->n_spheres - s->n_mspheres; }
+    else if (id < s->n_spheres + s->n_mspheres + s->n_triangles) { r.type = 2; r.idx = id - s->n_spheres - s->n_mspheres; }
+    else { r.type = 3; r.idx = id - s->n_spheres - s->n_mspheres - s->n_triangles; }
     return r;
 }
 
@@ -223,7 +224,7 @@ static inline f3 msphere_center(const rrtb_msphere *m, float time)
  * u = un/det, v = vn/det the reference's  u<0 || u>1 || v<0 || u+v>1  is evaluated sign-aware.
  * t = float(tn) / float(det). */
 static inline double dcross(double a, double b, double c, double d) { return fma(a, b, -(c * d)); } /* a*b - c*d */
-static int triangle_t(f3 o, f3 d, f3 v0, f3 e1f, f3 e2f, float t_min, float t_max, float *t_out)
+static int triangle_t(f3 o, f3 d, double v0x, double v0y, double v0z, f3 e1f, f3 e2f, float t_min, float t_max, float *t_out)
 {
     const double EPS = (double)1e-7f;
     double e1x = e1f.x, e1y = e1f.y, e1z = e1f.z, e2x = e2f.x, e2y = e2f.y, e2z = e2f.z;
@@ -231,7 +232,7 @@ static int triangle_t(f3 o, f3 d, f3 v0, f3 e1f, f3 e2f, float t_min, float t_ma
     double hx = dcross(dy, e2z, dz, e2y), hy = dcross(dz, e2x, dx, e2z), hz = dcross(dx, e2y, dy, e2x);
     double det = fma(e1z, hz, fma(e1y, hy, e1x * hx));
     if (det > -EPS && det < EPS) return 0;
-    double sx = (double)o.x - (double)v0.x, sy = (double)o.y - (double)v0.y, sz = (double)o.z - (double)v0.z;
+    double sx = (double)o.x - v0x, sy = (double)o.y - v0y, sz = (double)o.z - v0z;
     double un = fma(sz, hz, fma(sy, hy, sx * hx));
     double qx = dcross(sy, e1z, sz, e1y), qy = dcross(sz, e1x, sx, e1z), qz = dcross(sx, e1y, sy, e1x);
     double vn = fma(dz, qz, fma(dy, qy, dx * qx));
@@ -258,6 +259,17 @@ static f3 triangle_normal(f3 v0, f3 v1, f3 v2)
     return unit3(cross3(unit3(sub3(v1, v0)), unit3(sub3(v2, v0))));
 }
 
+void orc_mtriangle_record(const rrtb_mtriangle *m, float base[3], float rate[3], float e1[3], float e2[3])
+{
+    float dt = m->time1 - m->time0;
+    for (int k = 0; k < 3; ++k) {
+        rate[k] = m->delta[k] / dt;
+        base[k] = fmaf(-rate[k], m->time0, m->v0[k]);
+        e1[k] = m->v1[k] - m->v0[k];
+        e2[k] = m->v2[k] - m->v0[k];
+    }
+}
+
 void orc_triangle_normal(const rrtb_triangle *tr, float n[3])
 {
     f3 v = triangle_normal(ld3(tr->v0), ld3(tr->v1), ld3(tr->v2));
@@ -277,8 +289,17 @@ static int hit_t_only(const orc_scene *s, int id, f3 o, f3 d, float time, float 
         const rrtb_msphere *m = &s->mspheres[r.idx];
         return sphere_roots(o, d, msphere_center(m, time), m->radius, t_min, t_max, t);
     }
-    const rrtb_triangle *tr = &s->triangles[r.idx];
-    return triangle_t(o, d, ld3(tr->v0), sub3(ld3(tr->v1), ld3(tr->v0)), sub3(ld3(tr->v2), ld3(tr->v0)), t_min, t_max, t);
+    if (r.type == 2) {
+        const rrtb_triangle *tr = &s->triangles[r.idx];
+        return triangle_t(o, d, (double)tr->v0[0], (double)tr->v0[1], (double)tr->v0[2], sub3(ld3(tr->v1), ld3(tr->v0)),
+                          sub3(ld3(tr->v2), ld3(tr->v0)), t_min, t_max, t);
+    }
+    /* the instance translates, so the ray meets the triangle whose v0 is v0(time); edges unchanged */
+    float base[3], rate[3], e1[3], e2[3];
+    orc_mtriangle_record(&s->mtriangles[r.idx], base, rate, e1, e2);
+    double tm = (double)time;
+    return triangle_t(o, d, fma((double)rate[0], tm, (double)base[0]), fma((double)rate[1], tm, (double)base[1]),
+                      fma((double)rate[2], tm, (double)base[2]), ld3(e1), ld3(e2), t_min, t_max, t);
 }
 
 /* hit_record fill: sphere.h:51-55, moving_sphere.h:51-55, triangle.h:62-66, hittable.h:16-20 */
@@ -297,10 +318,15 @@ static void hit_record_fill(const orc_scene *s, int id, f3 o, f3 d, float time, 
         n = scl3(1.0f / m->radius, sub3(p, msphere_center(m, time)));
         *mat = m->material;
     }
-    else {
+    else if (r.type == 2) {
         const rrtb_triangle *tr = &s->triangles[r.idx];
         n = triangle_normal(ld3(tr->v0), ld3(tr->v1), ld3(tr->v2));
         *mat = tr->material;
+    }
+    else { /* a translation leaves the face normal alone */
+        const rrtb_mtriangle *m = &s->mtriangles[r.idx];
+        n = triangle_normal(ld3(m->v0), ld3(m->v1), ld3(m->v2));
+        *mat = m->material;
     }
     int front = dot3(d, n) < 0.0f;
     if (!front) n = F3(-n.x, -n.y, -n.z);
@@ -339,7 +365,7 @@ static inline int candidate_wins(const orc_scene *s, float t, int id, float bt, 
 
 static int closest_scan(const orc_scene *s, f3 o, f3 d, float time, float t_min, float *t_out, orc_counters *cnt)
 {
-    int n = s->n_spheres + s->n_mspheres + s->n_triangles;
+    int n = orc_n_objects(s);
     float best = INFINITY;
     int bid = -1;
     for (int id = 0; id < n; ++id) {
@@ -352,7 +378,7 @@ static int closest_scan(const orc_scene *s, f3 o, f3 d, float time, float t_min,
     if (cnt) {
         cnt->sphere_tests += (uint64_t)s->n_spheres;
         cnt->msphere_tests += (uint64_t)s->n_mspheres;
-        cnt->triangle_tests += (uint64_t)s->n_triangles;
+        cnt->triangle_tests += (uint64_t)s->n_triangles + (uint64_t)s->n_mtriangles;
     }
     *t_out = best;
     return bid;
@@ -404,11 +430,21 @@ static void prim_box(const orc_scene *s, int id, float *b)
             b[3 + k] = fmaxf(ca + m->radius, cb + m->radius);
         }
     }
-    else {
+    else if (r.type == 2) {
         const rrtb_triangle *t = &s->triangles[r.idx];
         for (int k = 0; k < 3; ++k) {
             b[k] = fminf(fminf(t->v0[k], t->v1[k]), t->v2[k]);
             b[3 + k] = fmaxf(fmaxf(t->v0[k], t->v1[k]), t->v2[k]);
+        }
+    }
+    else { /* union over the shutter interval of {v0(T), v0(T)+e1, v0(T)+e2}, T = camera time0 / time1 */
+        float base[3], rate[3], e1[3], e2[3];
+        orc_mtriangle_record(&s->mtriangles[r.idx], base, rate, e1, e2);
+        for (int k = 0; k < 3; ++k) {
+            float pa = fmaf(rate[k], s->cam.time0, base[k]), pb = fmaf(rate[k], s->cam.time1, base[k]);
+            float lo = fminf(pa, pb), hi = fmaxf(pa, pb);
+            b[k] = fminf(fminf(lo, lo + e1[k]), lo + e2[k]);
+            b[3 + k] = fmaxf(fmaxf(hi, hi + e1[k]), hi + e2[k]);
         }
     }
 }
@@ -438,7 +474,7 @@ static int cmp_u64(const void *a, const void *b)
 
 orc_bvh *orc_bvh_build(const orc_scene *s)
 {
-    int n = s->n_spheres + s->n_mspheres + s->n_triangles;
+    int n = orc_n_objects(s);
     orc_bvh *b = (orc_bvh *)calloc(1, sizeof(orc_bvh));
     b->n = n;
     b->morton = (uint32_t *)calloc((size_t)n, 4);

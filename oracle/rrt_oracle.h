@@ -28,6 +28,7 @@ typedef struct orc_scene {
     const rrtb_sphere *spheres;     int n_spheres;
     const rrtb_msphere *mspheres;   int n_mspheres;
     const rrtb_triangle *triangles; int n_triangles;
+    const rrtb_mtriangle *mtriangles; int n_mtriangles; /* translating instance triangles (ids after triangles) */
 } orc_scene;
 
 typedef struct orc_bvh {
@@ -87,6 +88,10 @@ void orc_path(const orc_scene *s, const orc_bvh *bvh, int W, int H, int pixel, i
 
 /* triangle.h:9-15: the float unit face normal the product stores in its leaf record */
 void orc_triangle_normal(const rrtb_triangle *tr, float n[3]);
+/* a moving triangle as the product's leaf record defines it (include/rrtb.h "rrtb_mtriangle"):
+ * rate[k] = delta[k] / (time1 - time0), base[k] = fma(-rate[k], time0, v0[k]); v0(time) = fma(rate, time, base) */
+void orc_mtriangle_record(const rrtb_mtriangle *m, float base[3], float rate[3], float e1[3], float e2[3]);
+static inline int orc_n_objects(const orc_scene *s) { return s->n_spheres + s->n_mspheres + s->n_triangles + s->n_mtriangles; }
 
 /* ---- the DOUBLE integrator (rrt_oracle_f64.c): FP_T = double semantics over the same float scene ---- */
 void orc_d_camera_ray(const rrtb_camera *cam, int W, int H, int pixel, int sample, uint64_t seed, double *ray7);

@@ -115,15 +115,10 @@ static d3 msphere_center_d(const rrtb_msphere *m, double time)
 }
 
 /* triangle.h:35-75 in double; edges from the float-rounded e1, e2 the product stores */
-static int triangle_d(d3 o, d3 d, const rrtb_triangle *tr, double t_min, double t_max, double *t_out)
+static int triangle_d(d3 o, d3 d, d3 v0, const float e1f[3], const float e2f[3], double t_min, double t_max, double *t_out)
 {
     const double EPS = 1e-7;
-    float e1f[3], e2f[3];
-    for (int k = 0; k < 3; ++k) {
-        e1f[k] = tr->v1[k] - tr->v0[k];
-        e2f[k] = tr->v2[k] - tr->v0[k];
-    }
-    d3 e1 = ldf(e1f), e2 = ldf(e2f), v0 = ldf(tr->v0);
+    d3 e1 = ldf(e1f), e2 = ldf(e2f);
     d3 h = D3(dcr(d.y, e2.z, d.z, e2.y), dcr(d.z, e2.x, d.x, e2.z), dcr(d.x, e2.y, d.y, e2.x));
     double det = ddot(e1, h);
     if (det > -EPS && det < EPS) return 0;
@@ -145,7 +140,12 @@ static int triangle_d(d3 o, d3 d, const rrtb_triangle *tr, double t_min, double 
     return 0;
 }
 
-static int obj_type(const orc_scene *s, int id) { return id < s->n_spheres ? 0 : (id < s->n_spheres + s->n_mspheres ? 1 : 2); }
+static int obj_type(const orc_scene *s, int id)
+{
+    if (id < s->n_spheres) return 0;
+    if (id < s->n_spheres + s->n_mspheres) return 1;
+    return id < s->n_spheres + s->n_mspheres + s->n_triangles ? 2 : 3;
+}
 
 static int hit_d(const orc_scene *s, int id, d3 o, d3 d, double time, double t_min, double t_max, double *t)
 {
@@ -158,14 +158,27 @@ static int hit_d(const orc_scene *s, int id, d3 o, d3 d, double time, double t_m
         const rrtb_msphere *m = &s->mspheres[id - s->n_spheres];
         return sphere_d(o, d, msphere_center_d(m, time), (double)m->radius, t_min, t_max, t);
     }
-    return triangle_d(o, d, &s->triangles[id - s->n_spheres - s->n_mspheres], t_min, t_max, t);
+    if (ty == 2) {
+        const rrtb_triangle *tr = &s->triangles[id - s->n_spheres - s->n_mspheres];
+        float e1[3], e2[3];
+        for (int k = 0; k < 3; ++k) {
+            e1[k] = tr->v1[k] - tr->v0[k];
+            e2[k] = tr->v2[k] - tr->v0[k];
+        }
+        return triangle_d(o, d, ldf(tr->v0), e1, e2, t_min, t_max, t);
+    }
+    float base[3], rate[3], e1[3], e2[3]; /* v0(time) = fma(rate, time, base) */
+    orc_mtriangle_record(&s->mtriangles[id - s->n_spheres - s->n_mspheres - s->n_triangles], base, rate, e1, e2);
+    d3 v0 = D3(fma((double)rate[0], time, (double)base[0]), fma((double)rate[1], time, (double)base[1]),
+               fma((double)rate[2], time, (double)base[2]));
+    return triangle_d(o, d, v0, e1, e2, t_min, t_max, t);
 }
 
 static int wins_d(const orc_scene *s, double t, int id, double bt, int bid)
 {
     if (bid < 0 || t < bt) return 1;
     if (t > bt) return 0;
-    int ct = obj_type(s, id) == 2, bt_tri = obj_type(s, bid) == 2;
+    int ct = obj_type(s, id) >= 2, bt_tri = obj_type(s, bid) >= 2;
     if (ct != bt_tri) return !ct;
     return ct ? (id < bid) : (id > bid);
 }
@@ -197,10 +210,19 @@ static void record_d(const orc_scene *s, int id, d3 o, d3 d, double time, double
         n = D3(inv * (p.x - c.x), inv * (p.y - c.y), inv * (p.z - c.z));
         *mat = m->material;
     }
-    else {
+    else if (ty == 2) {
         const rrtb_triangle *tr = &s->triangles[id - s->n_spheres - s->n_mspheres];
         n = tri_normal_f(tr);
         *mat = tr->material;
+    }
+    else {
+        const rrtb_mtriangle *m = &s->mtriangles[id - s->n_spheres - s->n_mspheres - s->n_triangles];
+        rrtb_triangle tr;
+        memcpy(tr.v0, m->v0, 12);
+        memcpy(tr.v1, m->v1, 12);
+        memcpy(tr.v2, m->v2, 12);
+        n = tri_normal_f(&tr);
+        *mat = m->material;
     }
     int front = (d.x * n.x + d.y * n.y) + d.z * n.z < 0.0;
     if (!front) n = D3(-n.x, -n.y, -n.z);
@@ -224,7 +246,7 @@ static int box_hit_f(const float *bx, float pad, const float inv[3], const float
  * padded boxes (conservative: the padding is 16x the rounding of the ray), the leaf tests in double. */
 static int closest_d(const orc_scene *s, const orc_bvh *b, d3 o, d3 d, double time, double t_min, double *t_out)
 {
-    int n = s->n_spheres + s->n_mspheres + s->n_triangles;
+    int n = orc_n_objects(s);
     double best = INFINITY;
     int bid = -1;
     if (!b || n < 2) {

@@ -19,6 +19,7 @@ from .types import (
     camera_dtype,
     material_dtype,
     msphere_dtype,
+    mtriangle_dtype,
     sphere_dtype,
     triangle_dtype,
 )
@@ -77,6 +78,7 @@ class Scene:
                 grab(lib.rrtb_scene_spheres(h), ns, sphere_dtype),
                 grab(lib.rrtb_scene_mspheres(h), nms, msphere_dtype),
                 grab(lib.rrtb_scene_triangles(h), nt, triangle_dtype),
+                grab(lib.rrtb_scene_mtriangles(h), lib.rrtb_scene_mtriangle_count(h), mtriangle_dtype),
             )
         finally:
             lib.rrtb_scene_free(h)
@@ -154,6 +156,8 @@ class Context:
     # -- scene ------------------------------------------------------------------------------------------
     def set_scene(self, scene, use_bvh=True):
         a = scene.arrays if isinstance(scene, Scene) else scene
+        # moving triangles are staged, then consumed by rrtb_scene_set
+        self._check(self.lib.rrtb_scene_stage_moving_triangles(self.h, _vp(a.mtriangles), len(a.mtriangles)))
         self._check(
             self.lib.rrtb_scene_set(
                 self.h, _vp(a.camera), _vp(a.materials), len(a.materials), _vp(a.spheres), len(a.spheres),

@@ -28,7 +28,8 @@ int cuda_fail(rrtb_ctx *ctx, cudaError_t e, const char *expr, const char *file, 
     return RRTB_ERR_CUDA;
 }
 
-int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_msphere *d_msph, const rrtb_triangle *d_tri);
+int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_msphere *d_msph, const rrtb_triangle *d_tri,
+                      const rrtb_mtriangle *d_mtri);
 
 static int invalid(rrtb_ctx *ctx, const char *msg)
 {
@@ -141,14 +142,27 @@ int rrtb_device_info(rrtb_ctx *ctx, int64_t *out4, char *name, int name_len)
     return RRTB_OK;
 }
 
+int rrtb_scene_stage_moving_triangles(rrtb_ctx *ctx, const rrtb_mtriangle *mtriangles, int n_mtriangles)
+{
+    if (!ctx || n_mtriangles < 0 || (n_mtriangles > 0 && !mtriangles)) return RRTB_ERR_INVALID;
+    for (int i = 0; i < n_mtriangles; ++i)
+        if (!(mtriangles[i].time1 != mtriangles[i].time0)) return invalid(ctx, "moving triangle needs time0 != time1");
+    ctx->staged_mtriangles.assign(mtriangles, mtriangles + n_mtriangles);
+    return RRTB_OK;
+}
+
 int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *materials, int n_materials,
                    const rrtb_sphere *spheres, int n_spheres, const rrtb_msphere *mspheres, int n_mspheres,
                    const rrtb_triangle *triangles, int n_triangles, int use_bvh)
 {
     if (!ctx) return RRTB_ERR_INVALID;
+    // staged moving triangles belong to this call whether it succeeds or not
+    std::vector<rrtb_mtriangle> mtri;
+    mtri.swap(ctx->staged_mtriangles);
+    const int n_mtriangles = (int)mtri.size();
     if (!cam || !materials || n_materials <= 0) return invalid(ctx, "scene needs a camera and at least one material");
     if (n_spheres < 0 || n_mspheres < 0 || n_triangles < 0) return invalid(ctx, "negative primitive count");
-    const long long n_ll = (long long)n_spheres + n_mspheres + n_triangles;
+    const long long n_ll = (long long)n_spheres + n_mspheres + n_triangles + n_mtriangles;
     if (n_ll <= 0) return invalid(ctx, "scene has no objects");
     if (n_ll >= (1ll << 29)) return invalid(ctx, "too many primitives (limit 2^29)");
     if ((n_spheres && !spheres) || (n_mspheres && !mspheres) || (n_triangles && !triangles))
@@ -160,6 +174,8 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
         if (mspheres[i].material < 0 || mspheres[i].material >= n_materials) return invalid(ctx, "msphere material index out of range");
     for (int i = 0; i < n_triangles; ++i)
         if (triangles[i].material < 0 || triangles[i].material >= n_materials) return invalid(ctx, "triangle material index out of range");
+    for (int i = 0; i < n_mtriangles; ++i)
+        if (mtri[i].material < 0 || mtri[i].material >= n_materials) return invalid(ctx, "moving triangle material index out of range");
 
     RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
     free_scene(ctx);
@@ -168,6 +184,7 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     ctx->n_spheres = n_spheres;
     ctx->n_mspheres = n_mspheres;
     ctx->n_triangles = n_triangles;
+    ctx->n_mtriangles = n_mtriangles;
     ctx->n_prims = n;
     ctx->use_bvh = use_bvh ? 1 : 0;
 
@@ -209,10 +226,12 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     rrtb_sphere *d_sph = nullptr;
     rrtb_msphere *d_msph = nullptr;
     rrtb_triangle *d_tri = nullptr;
+    rrtb_mtriangle *d_mtri = nullptr;
     auto cleanup = [&]() {
         if (d_sph) cudaFree(d_sph);
         if (d_msph) cudaFree(d_msph);
         if (d_tri) cudaFree(d_tri);
+        if (d_mtri) cudaFree(d_mtri);
     };
     cudaStream_t st = ctx->stream;
 #define SET_CUDA(expr)                                                      \
@@ -238,7 +257,11 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
         SET_CUDA(cudaMalloc((void **)&d_tri, sizeof(rrtb_triangle) * (size_t)n_triangles));
         SET_CUDA(cudaMemcpyAsync(d_tri, triangles, sizeof(rrtb_triangle) * (size_t)n_triangles, cudaMemcpyHostToDevice, st));
     }
-    rc = prepare_and_build(ctx, d_sph, d_msph, d_tri);
+    if (n_mtriangles) {
+        SET_CUDA(cudaMalloc((void **)&d_mtri, sizeof(rrtb_mtriangle) * (size_t)n_mtriangles));
+        SET_CUDA(cudaMemcpyAsync(d_mtri, mtri.data(), sizeof(rrtb_mtriangle) * (size_t)n_mtriangles, cudaMemcpyHostToDevice, st));
+    }
+    rc = prepare_and_build(ctx, d_sph, d_msph, d_tri, d_mtri);
     if (rc) {
         cleanup();
         return rc;
@@ -261,8 +284,8 @@ int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam)
         ctx->err = "no scene";
         return RRTB_ERR_NO_SCENE;
     }
-    if (ctx->n_mspheres > 0 && (cam->time0 != ctx->cam.time0 || cam->time1 != ctx->cam.time1))
-        return invalid(ctx, "shutter interval changed with moving spheres present: call rrtb_scene_set");
+    if (ctx->n_mspheres + ctx->n_mtriangles > 0 && (cam->time0 != ctx->cam.time0 || cam->time1 != ctx->cam.time1))
+        return invalid(ctx, "shutter interval changed with moving primitives present: call rrtb_scene_set");
     ctx->cam = *cam;
     return RRTB_OK;
 }

@@ -43,26 +43,15 @@ __device__ __forceinline__ float warp_max(float v)
     return v;
 }
 
-__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz)
-{
-    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
-}
-__device__ __forceinline__ void unit3_rn(float &x, float &y, float &z)
-{
-    float inv = __fdiv_rn(1.0f, __fsqrt_rn(dot3_rn(x, y, z, x, y, z)));
-    x = __fmul_rn(inv, x);
-    y = __fmul_rn(inv, y);
-    z = __fmul_rn(inv, z);
-}
-
 // One thread per object id.  partial[b*7 + 0..2] = centroid min, 3..5 = centroid max, 6 = max |coordinate|
 __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__ sph, int ns,
                                                   const rrtb_msphere *__restrict__ msph, int nms,
-                                                  const rrtb_triangle *__restrict__ tri, int nt, float cam_t0,
+                                                  const rrtb_triangle *__restrict__ tri, int nt,
+                                                  const rrtb_mtriangle *__restrict__ mtri, int nmt, float cam_t0,
                                                   float cam_t1, float4 *__restrict__ prim, int2 *__restrict__ info,
                                                   float *__restrict__ prim_box, float *__restrict__ partial)
 {
-    const int n = ns + nms + nt;
+    const int n = ns + nms + nt + nmt;
     const int id = blockIdx.x * TPB + threadIdx.x;
     const float inf = __int_as_float(0x7f800000);
     float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
@@ -96,7 +85,7 @@ __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__
             c = make_float4(dt, 0.f, 0.f, 0.f);
             mat = m.material;
         }
-        else {
+        else if (id < ns + nms + nt) {
             rrtb_triangle t = tri[id - ns - nms];
             float e1[3], e2[3];
             for (int k = 0; k < 3; ++k) {
@@ -105,17 +94,31 @@ __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__
                 mn[k] = fminf(fminf(t.v0[k], t.v1[k]), t.v2[k]);
                 mx[k] = fmaxf(fmaxf(t.v0[k], t.v1[k]), t.v2[k]);
             }
-            // triangle.h:9-15: unit(cross(unit(v1-v0), unit(v2-v0)))
-            float ax = e1[0], ay = e1[1], az = e1[2], bx = e2[0], by = e2[1], bz = e2[2];
-            unit3_rn(ax, ay, az);
-            unit3_rn(bx, by, bz);
-            float nx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
-            float ny = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
-            float nz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
-            unit3_rn(nx, ny, nz);
+            float nx, ny, nz;
+            triangle_unit_normal(e1[0], e1[1], e1[2], e2[0], e2[1], e2[2], nx, ny, nz);
             a = make_float4(t.v0[0], t.v0[1], t.v0[2], nx);
             b = make_float4(e1[0], e1[1], e1[2], ny);
             c = make_float4(e2[0], e2[1], e2[2], nz);
+            mat = t.material;
+        }
+        else { // translating instance triangle, include/rrtb.h "rrtb_mtriangle"
+            rrtb_mtriangle t = mtri[id - ns - nms - nt];
+            float dt = __fsub_rn(t.time1, t.time0);
+            float base[3], rate[3], e1[3], e2[3];
+            for (int k = 0; k < 3; ++k) {
+                rate[k] = __fdiv_rn(t.delta[k], dt);
+                base[k] = __fmaf_rn(-rate[k], t.time0, t.v0[k]);
+                e1[k] = __fsub_rn(t.v1[k], t.v0[k]);
+                e2[k] = __fsub_rn(t.v2[k], t.v0[k]);
+                // union over the shutter interval of {v0(T), v0(T)+e1, v0(T)+e2}, T = camera time0 / time1
+                float pa = __fmaf_rn(rate[k], cam_t0, base[k]), pb = __fmaf_rn(rate[k], cam_t1, base[k]);
+                float lo = fminf(pa, pb), hi = fmaxf(pa, pb);
+                mn[k] = fminf(fminf(lo, __fadd_rn(lo, e1[k])), __fadd_rn(lo, e2[k]));
+                mx[k] = fmaxf(fmaxf(hi, __fadd_rn(hi, e1[k])), __fadd_rn(hi, e2[k]));
+            }
+            a = make_float4(base[0], base[1], base[2], rate[0]);
+            b = make_float4(e1[0], e1[1], e1[2], rate[1]);
+            c = make_float4(e2[0], e2[1], e2[2], rate[2]);
             mat = t.material;
         }
         prim[3 * id + 0] = a;
@@ -388,9 +391,12 @@ __device__ __forceinline__ void center_half(float lo, float hi, float pad, float
     h = fmaxf(hi - c, c - lo) + pad;
 }
 
-__device__ __forceinline__ int prim_type(int id, int ns, int nms) { return id < ns ? PRIM_SPHERE : (id < ns + nms ? PRIM_MSPHERE : PRIM_TRIANGLE); }
+__device__ __forceinline__ int prim_type(int id, int ns, int nms, int nt)
+{
+    return id < ns ? PRIM_SPHERE : (id < ns + nms ? PRIM_MSPHERE : (id < ns + nms + nt ? PRIM_TRIANGLE : PRIM_MTRIANGLE));
+}
 
-__global__ void __launch_bounds__(TPB) k_flatten_nodes(const uint64_t *__restrict__ keys, int n, int ns, int nms,
+__global__ void __launch_bounds__(TPB) k_flatten_nodes(const uint64_t *__restrict__ keys, int n, int ns, int nms, int nt,
                                                         const int *__restrict__ left, const int *__restrict__ right,
                                                         const float *__restrict__ prim_box,
                                                         const float *__restrict__ node_box,
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(TPB) k_flatten_nodes(const uint64_t *__restric
             const float *b = prim_box;
             float c[3], h[3];
             for (int k = 0; k < 3; ++k) center_half(b[k], b[3 + k], pad, c[k], h[k]);
-            int enc = ~((0 << 2) | prim_type(0, ns, nms));
+            int enc = ~((0 << 2) | prim_type(0, ns, nms, nt));
             nodes[0] = make_float4(c[0], c[1], c[2], h[0]);
             nodes[1] = make_float4(h[1], h[2], c[0], c[1]);
             nodes[2] = make_float4(c[2], h[0], h[1], h[2]);
@@ -426,7 +432,7 @@ __global__ void __launch_bounds__(TPB) k_flatten_nodes(const uint64_t *__restric
             int slot = ~ref[c];
             int id = (int)(uint32_t)keys[slot];
             b = prim_box + 6 * id;
-            enc[c] = ~((slot << 2) | prim_type(id, ns, nms));
+            enc[c] = ~((slot << 2) | prim_type(id, ns, nms, nt));
         }
         for (int k = 0; k < 3; ++k) center_half(b[k], b[3 + k], pad, bx[c][k], bx[c][3 + k]);
     }
@@ -485,7 +491,8 @@ __global__ void k_build_top(const float4 *__restrict__ nodes, int n_internal, fl
 }
 
 // exposed to rrtb_api.cu (scene upload): raw struct arrays are staged by the caller
-int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_msphere *d_msph, const rrtb_triangle *d_tri)
+int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_msphere *d_msph, const rrtb_triangle *d_tri,
+                      const rrtb_mtriangle *d_mtri)
 {
     const int n = ctx->n_prims;
     const int ns = ctx->n_spheres, nms = ctx->n_mspheres, nt = ctx->n_triangles;
@@ -493,7 +500,7 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
     cudaStream_t st = ctx->stream;
     BuildConsts *bc = (BuildConsts *)(ctx->d_reduce + (size_t)nb * 7);
 
-    k_prepare<<<nb, TPB, 0, st>>>(d_sph, ns, d_msph, nms, d_tri, nt, ctx->cam.time0, ctx->cam.time1, ctx->d_prim,
+    k_prepare<<<nb, TPB, 0, st>>>(d_sph, ns, d_msph, nms, d_tri, nt, d_mtri, ctx->n_mtriangles, ctx->cam.time0, ctx->cam.time1, ctx->d_prim,
                                   ctx->d_prim_info, ctx->d_prim_box, ctx->d_reduce);
     float cam_mag = 0.f;
     for (int k = 0; k < 3; ++k) cam_mag = fmaxf(cam_mag, fabsf(ctx->cam.origin[k]) + ctx->cam.lens_radius);
@@ -529,7 +536,7 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
         RRTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_parent, &m1, sizeof(int), cudaMemcpyHostToDevice, st));
     }
     const int nbn = (max(n - 1, 1) + TPB - 1) / TPB;
-    k_flatten_nodes<<<nbn, TPB, 0, st>>>(ctx->d_keys, n, ns, nms, ctx->d_left, ctx->d_right, ctx->d_prim_box,
+    k_flatten_nodes<<<nbn, TPB, 0, st>>>(ctx->d_keys, n, ns, nms, nt, ctx->d_left, ctx->d_right, ctx->d_prim_box,
                                          ctx->d_node_box, bc, ctx->d_nodes);
     k_flatten_leaves<<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_prim, ctx->d_prim_info, ctx->d_leaves,
                                          ctx->d_leaf_info);

@@ -40,12 +40,14 @@ __device__ unsigned int g_rrtb_violations;
 //   sphere         a = (c.xyz, r)
 //   moving sphere  a = (c0.xyz, r)   b = (c1-c0 .xyz, t0)   c = (t1-t0, -, -, -)
 //   triangle       a = (v0.xyz, n.x) b = (e1.xyz, n.y)      c = (e2.xyz, n.z)    n = unit face normal
+//   moving tri.    a = (base.xyz, rate.x) b = (e1.xyz, rate.y) c = (e2.xyz, rate.z)   v0(time) = fma(rate, time, base)
+//                  (include/rrtb.h "rrtb_mtriangle"; the normal is recomputed at shading time)
 // leaf_info[k] = (object id, material index)
 // BVH node: 4 x float4 (64 B): padded boxes of both children + child refs
 //   n0 = (L.c.xyz, L.h.x)  n1 = (L.h.y, L.h.z, R.c.x, R.c.y)  n2 = (R.c.z, R.h.xyz)   c = centre, h = half extent
 //   n3 = (bits(left ref), bits(right ref), -, -)
 // child ref >= 0: internal node index;  < 0: leaf, ~ref = (leaf slot << 2) | type
-enum : int { PRIM_SPHERE = 0, PRIM_MSPHERE = 1, PRIM_TRIANGLE = 2 };
+enum : int { PRIM_SPHERE = 0, PRIM_MSPHERE = 1, PRIM_TRIANGLE = 2, PRIM_MTRIANGLE = 3 };
 
 struct DeviceScene {
     const float4 *nodes;     // [4 * max(n-1,1)]
@@ -57,7 +59,7 @@ struct DeviceScene {
     const int2 *flat_info;   // [n]
     const float4 *materials; // [nm] (albedo.xyz, param)
     const int *material_type;// [nm]
-    int n_prims, n_spheres, n_mspheres, n_triangles;
+    int n_prims, n_spheres, n_mspheres, n_triangles, n_mtriangles;
     int use_bvh;
 };
 
@@ -254,9 +256,33 @@ __device__ __forceinline__ double dcross(double a, double b, double c, double d)
     return __fma_rn(a, b, -__dmul_rn(c, d));
 }
 
-// triangle.h:35-75: Moeller-Trumbore, numerators in double, division-free barycentric tests, exclusive range
-__device__ __forceinline__ bool triangle_test(const Ray &r, float4 A, float4 B, float4 C, float t_min, float t_max,
-                                              float &t_out)
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+__device__ __forceinline__ void unit3_rn(float &x, float &y, float &z)
+{
+    float inv = __fdiv_rn(1.0f, __fsqrt_rn(dot3_rn(x, y, z, x, y, z)));
+    x = __fmul_rn(inv, x);
+    y = __fmul_rn(inv, y);
+    z = __fmul_rn(inv, z);
+}
+// triangle.h:9-15: unit(cross(unit(v1-v0), unit(v2-v0)))
+__device__ __forceinline__ void triangle_unit_normal(float ax, float ay, float az, float bx, float by, float bz, float &nx,
+                                                     float &ny, float &nz)
+{
+    unit3_rn(ax, ay, az);
+    unit3_rn(bx, by, bz);
+    nx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
+    ny = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
+    nz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+    unit3_rn(nx, ny, nz);
+}
+
+// triangle.h:35-75: Moeller-Trumbore, numerators in double, division-free barycentric tests, exclusive range.
+// (v0x, v0y, v0z) is the first vertex in double: the stored one, or v0(time) of a translating instance triangle.
+__device__ __forceinline__ bool triangle_test(const Ray &r, double v0x, double v0y, double v0z, float4 B, float4 C,
+                                              float t_min, float t_max, float &t_out)
 {
     const double EPS = (double)1e-7f;
     double e1x = B.x, e1y = B.y, e1z = B.z, e2x = C.x, e2y = C.y, e2z = C.z;
@@ -264,8 +290,7 @@ __device__ __forceinline__ bool triangle_test(const Ray &r, float4 A, float4 B, 
     double hx = dcross(dy, e2z, dz, e2y), hy = dcross(dz, e2x, dx, e2z), hz = dcross(dx, e2y, dy, e2x);
     double det = __fma_rn(e1z, hz, __fma_rn(e1y, hy, __dmul_rn(e1x, hx)));
     if (det > -EPS && det < EPS) return false;
-    double sx = __dsub_rn((double)r.ox, (double)A.x), sy = __dsub_rn((double)r.oy, (double)A.y),
-           sz = __dsub_rn((double)r.oz, (double)A.z);
+    double sx = __dsub_rn((double)r.ox, v0x), sy = __dsub_rn((double)r.oy, v0y), sz = __dsub_rn((double)r.oz, v0z);
     double un = __fma_rn(sz, hz, __fma_rn(sy, hy, __dmul_rn(sx, hx)));
     double qx = dcross(sy, e1z, sz, e1y), qy = dcross(sz, e1x, sx, e1z), qz = dcross(sx, e1y, sy, e1x);
     double vn = __fma_rn(dz, qz, __fma_rn(dy, qy, __dmul_rn(dx, qx)));
@@ -294,7 +319,7 @@ __device__ __forceinline__ bool candidate_wins(float t, int type, int obj, float
     if (bobj < 0) return true;
     if (t < bt) return true;
     if (t > bt) return false;
-    bool ct = type == PRIM_TRIANGLE, bt_tri = btype == PRIM_TRIANGLE;
+    bool ct = type >= PRIM_TRIANGLE, bt_tri = btype >= PRIM_TRIANGLE; // moving triangles are triangles
     if (ct != bt_tri) return !ct;
     return ct ? (obj < bobj) : (obj > bobj);
 }
@@ -324,7 +349,14 @@ __device__ __forceinline__ void leaf_test(const float4 *__restrict__ leaves, con
     }
     else {
         float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
-        h = triangle_test(r, a, b, c, t_min, best.t, t);
+        double v0x = a.x, v0y = a.y, v0z = a.z;
+        if (type == PRIM_MTRIANGLE) { // the instance translates: meet the triangle where it is at the ray's time
+            double tm = r.tm;
+            v0x = __fma_rn((double)a.w, tm, v0x);
+            v0y = __fma_rn((double)b.w, tm, v0y);
+            v0z = __fma_rn((double)c.w, tm, v0z);
+        }
+        h = triangle_test(r, v0x, v0y, v0z, b, c, t_min, best.t, t);
     }
     if (!h) return;
     if (best.ref >= 0 && t == best.t) { // exact tie: resolve by object id (rare path)
@@ -345,9 +377,9 @@ __device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, 
     best.t = __int_as_float(0x7f800000);
     best.ref = -1;
     best.obj = -1;
-    const int n0 = s.n_spheres, n1 = n0 + s.n_mspheres, n = s.n_prims;
+    const int n0 = s.n_spheres, n1 = n0 + s.n_mspheres, n2 = n1 + s.n_triangles, n = s.n_prims;
     for (int k = 0; k < n; ++k) {
-        int type = k < n0 ? PRIM_SPHERE : (k < n1 ? PRIM_MSPHERE : PRIM_TRIANGLE);
+        int type = k < n0 ? PRIM_SPHERE : (k < n1 ? PRIM_MSPHERE : (k < n2 ? PRIM_TRIANGLE : PRIM_MTRIANGLE));
         leaf_test<COUNT>(s.flat_leaves, s.flat_info, k, type, r, p, t_min, best, cnt);
     }
     return best;
@@ -452,6 +484,10 @@ __device__ __forceinline__ HitRecord hit_record(const float4 *__restrict__ leave
         rec.nx = a.w;
         rec.ny = b.w;
         rec.nz = c.w;
+    }
+    else if (type == PRIM_MTRIANGLE) { // a translation leaves the face normal alone; the record has no room for it
+        float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+        triangle_unit_normal(b.x, b.y, b.z, c.x, c.y, c.z, rec.nx, rec.ny, rec.nz);
     }
     else {
         float cx = a.x, cy = a.y, cz = a.z;

@@ -139,15 +139,15 @@ __device__ __forceinline__ void msphere_center_d(float4 a, float4 b, float4 c, d
 }
 
 // triangle.h:35-75 in double
-__device__ __forceinline__ bool triangle_test_d(const RayD &r, float4 A, float4 B, float4 C, double t_min, double t_max,
-                                                double &t_out)
+__device__ __forceinline__ bool triangle_test_d(const RayD &r, double v0x, double v0y, double v0z, float4 B, float4 C,
+                                                double t_min, double t_max, double &t_out)
 {
     const double EPS = 1e-7;
     double e1x = B.x, e1y = B.y, e1z = B.z, e2x = C.x, e2y = C.y, e2z = C.z;
     double hx = dcross(r.dy, e2z, r.dz, e2y), hy = dcross(r.dz, e2x, r.dx, e2z), hz = dcross(r.dx, e2y, r.dy, e2x);
     double det = ddot3(e1x, e1y, e1z, hx, hy, hz);
     if (det > -EPS && det < EPS) return false;
-    double sx = __dsub_rn(r.ox, (double)A.x), sy = __dsub_rn(r.oy, (double)A.y), sz = __dsub_rn(r.oz, (double)A.z);
+    double sx = __dsub_rn(r.ox, v0x), sy = __dsub_rn(r.oy, v0y), sz = __dsub_rn(r.oz, v0z);
     double un = ddot3(sx, sy, sz, hx, hy, hz);
     double qx = dcross(sy, e1z, sz, e1y), qy = dcross(sz, e1x, sx, e1z), qz = dcross(sx, e1y, sy, e1x);
     double vn = ddot3(r.dx, r.dy, r.dz, qx, qy, qz);
@@ -188,7 +188,13 @@ __device__ __forceinline__ void leaf_test_d(const float4 *__restrict__ leaves, c
     }
     else {
         float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
-        h = triangle_test_d(r, a, b, c, t_min, best.t, t);
+        double v0x = a.x, v0y = a.y, v0z = a.z;
+        if (type == PRIM_MTRIANGLE) {
+            v0x = __fma_rn((double)a.w, r.tm, v0x);
+            v0y = __fma_rn((double)b.w, r.tm, v0y);
+            v0z = __fma_rn((double)c.w, r.tm, v0z);
+        }
+        h = triangle_test_d(r, v0x, v0y, v0z, b, c, t_min, best.t, t);
     }
     if (!h) return;
     if (best.ref >= 0 && t == best.t) { // exact tie: the float integrator's rule, by object id
@@ -206,9 +212,9 @@ __device__ __forceinline__ HitD closest_scan_d(const DeviceScene &s, const RayD 
     HitD best;
     best.t = __longlong_as_double(0x7ff0000000000000ll);
     best.ref = -1;
-    const int n0 = s.n_spheres, n1 = n0 + s.n_mspheres, n = s.n_prims;
+    const int n0 = s.n_spheres, n1 = n0 + s.n_mspheres, n2 = n1 + s.n_triangles, n = s.n_prims;
     for (int k = 0; k < n; ++k) {
-        int type = k < n0 ? PRIM_SPHERE : (k < n1 ? PRIM_MSPHERE : PRIM_TRIANGLE);
+        int type = k < n0 ? PRIM_SPHERE : (k < n1 ? PRIM_MSPHERE : (k < n2 ? PRIM_TRIANGLE : PRIM_MTRIANGLE));
         leaf_test_d<COUNT>(s.flat_leaves, s.flat_info, k, type, r, t_min, best, cnt);
     }
     return best;
@@ -254,6 +260,14 @@ __device__ __forceinline__ HitRecordD hit_record_d(const float4 *__restrict__ le
         rec.nx = (double)a.w;
         rec.ny = (double)b.w;
         rec.nz = (double)c.w;
+    }
+    else if (type == PRIM_MTRIANGLE) {
+        float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+        float nx, ny, nz;
+        triangle_unit_normal(b.x, b.y, b.z, c.x, c.y, c.z, nx, ny, nz);
+        rec.nx = (double)nx;
+        rec.ny = (double)ny;
+        rec.nz = (double)nz;
     }
     else {
         double cx = a.x, cy = a.y, cz = a.z;

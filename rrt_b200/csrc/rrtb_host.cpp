@@ -75,6 +75,8 @@ struct Obj {
 struct ObjInst {
     int obj, mat;
     std::vector<Xform> xf;
+    bool moving = false; // `mobj`: translates by delta between time0 and time1
+    float delta[3] = {0.f, 0.f, 0.f}, time0 = 0.f, time1 = 1.f;
 };
 
 struct ParseError {
@@ -123,6 +125,7 @@ struct rrtb_scene {
     std::vector<rrtb_sphere> spheres;
     std::vector<rrtb_msphere> mspheres;
     std::vector<rrtb_triangle> triangles;
+    std::vector<rrtb_mtriangle> mtriangles; // of `mobj` instances
     int n_objs = 0, n_obj_insts = 0;
 };
 
@@ -310,14 +313,23 @@ int rrtb_scene_parse_file(const char *path, int image_width, int image_height, r
                 objs.push_back(cur);
                 open_obj = false;
             }
-            else if (line.find("obj") == 0) { // scene.h:387-427
+            else if (line.find("obj") == 0 || line.find("mobj") == 0) { // scene.h:387-427; mobj: include/rrtb.h
+                const bool moving = line[0] == 'm';
                 std::vector<std::string> w = words_of(line);
-                if (w.size() < 3)
+                if (w.size() < (moving ? 8u : 3u))
                     throw ParseError{1, "ERROR: obj called without enough args (count = " + std::to_string(w.size())};
                 ObjInst inst;
                 inst.obj = to_i(w[1]);
                 inst.mat = mat_idx[w[2]];
                 size_t idx = 3;
+                if (moving) {
+                    inst.moving = true;
+                    for (int k = 0; k < 3; ++k) inst.delta[k] = to_f(w[3 + k]);
+                    inst.time0 = to_f(w[6]);
+                    inst.time1 = to_f(w[7]);
+                    if (!(inst.time1 != inst.time0)) throw ParseError{1, "ERROR: mobj needs time0 != time1"};
+                    idx = 8;
+                }
                 while (idx < w.size() - 1) { // the words vector carries one trailing blank
                     char op = w[idx][0];
                     if (op == 't' || op == 's') {
@@ -357,7 +369,21 @@ int rrtb_scene_parse_file(const char *path, int image_width, int image_height, r
                     put(dst[q], v);
                 }
                 tr.material = in.mat;
-                sc->triangles.push_back(tr);
+                if (!in.moving) {
+                    sc->triangles.push_back(tr);
+                    continue;
+                }
+                rrtb_mtriangle mt{};
+                for (int k = 0; k < 3; ++k) {
+                    mt.v0[k] = tr.v0[k];
+                    mt.v1[k] = tr.v1[k];
+                    mt.v2[k] = tr.v2[k];
+                    mt.delta[k] = in.delta[k];
+                }
+                mt.time0 = in.time0;
+                mt.time1 = in.time1;
+                mt.material = in.mat;
+                sc->mtriangles.push_back(mt);
             }
         }
         // material indices produced by the name map are always valid except when the scene has a
@@ -393,10 +419,14 @@ const rrtb_material *rrtb_scene_materials(const rrtb_scene *s) { return s ? s->m
 const rrtb_sphere *rrtb_scene_spheres(const rrtb_scene *s) { return s ? s->spheres.data() : nullptr; }
 const rrtb_msphere *rrtb_scene_mspheres(const rrtb_scene *s) { return s ? s->mspheres.data() : nullptr; }
 const rrtb_triangle *rrtb_scene_triangles(const rrtb_scene *s) { return s ? s->triangles.data() : nullptr; }
+int rrtb_scene_mtriangle_count(const rrtb_scene *s) { return s ? (int)s->mtriangles.size() : 0; }
+const rrtb_mtriangle *rrtb_scene_mtriangles(const rrtb_scene *s) { return s ? s->mtriangles.data() : nullptr; }
 
 int rrtb_scene_upload(rrtb_ctx *ctx, const rrtb_scene *s, int use_bvh)
 {
     if (!ctx || !s) return RRTB_ERR_INVALID;
+    int rc = rrtb_scene_stage_moving_triangles(ctx, s->mtriangles.data(), (int)s->mtriangles.size());
+    if (rc != RRTB_OK) return rc;
     return rrtb_scene_set(ctx, &s->cam, s->materials.data(), (int)s->materials.size(), s->spheres.data(),
                           (int)s->spheres.size(), s->mspheres.data(), (int)s->mspheres.size(), s->triangles.data(),
                           (int)s->triangles.size(), use_bvh);

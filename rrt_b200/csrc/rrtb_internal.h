@@ -19,7 +19,8 @@ struct rrtb_ctx {
     // scene (host copies kept for camera updates / introspection)
     bool has_scene = false;
     rrtb_camera cam{};
-    int n_materials = 0, n_spheres = 0, n_mspheres = 0, n_triangles = 0, n_prims = 0;
+    int n_materials = 0, n_spheres = 0, n_mspheres = 0, n_triangles = 0, n_mtriangles = 0, n_prims = 0;
+    std::vector<rrtb_mtriangle> staged_mtriangles; // rrtb_scene_stage_moving_triangles -> next rrtb_scene_set
     int use_bvh = 1;
     double seconds_build = 0.0;
 

@@ -334,6 +334,7 @@ DeviceScene device_scene(const rrtb_ctx *ctx)
     s.n_spheres = ctx->n_spheres;
     s.n_mspheres = ctx->n_mspheres;
     s.n_triangles = ctx->n_triangles;
+    s.n_mtriangles = ctx->n_mtriangles;
     s.use_bvh = ctx->use_bvh;
     return s;
 }

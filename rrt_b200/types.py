@@ -31,8 +31,13 @@ msphere_dtype = np.dtype(
     [("center0", "<f4", 3), ("center1", "<f4", 3), ("time0", "<f4"), ("time1", "<f4"), ("radius", "<f4"), ("material", "<i4")]
 )
 triangle_dtype = np.dtype([("v0", "<f4", 3), ("v1", "<f4", 3), ("v2", "<f4", 3), ("material", "<i4")])
+# a triangle of a translating instance (vertices at time0, moves by delta until time1)
+mtriangle_dtype = np.dtype(
+    [("v0", "<f4", 3), ("v1", "<f4", 3), ("v2", "<f4", 3), ("delta", "<f4", 3), ("time0", "<f4"), ("time1", "<f4"), ("material", "<i4")]
+)
 
 assert camera_dtype.itemsize == 96
+assert mtriangle_dtype.itemsize == 60
 assert material_dtype.itemsize == 20
 assert sphere_dtype.itemsize == 20
 assert msphere_dtype.itemsize == 40
@@ -81,9 +86,9 @@ class Stats(C.Structure):
 
 class SceneArrays:
     """A scene as plain arrays, in the reference's object-id order (spheres, moving spheres, triangles;
-    rrt.cu:151-164)."""
+    rrt.cu:151-164), then the moving triangles of SURVEY 8f4."""
 
-    def __init__(self, camera, materials, spheres=None, mspheres=None, triangles=None):
+    def __init__(self, camera, materials, spheres=None, mspheres=None, triangles=None, mtriangles=None):
         self.camera = np.ascontiguousarray(np.asarray(camera, dtype=camera_dtype).reshape(1))
         self.materials = np.ascontiguousarray(np.asarray(materials, dtype=material_dtype))
         self.spheres = np.ascontiguousarray(
@@ -95,10 +100,13 @@ class SceneArrays:
         self.triangles = np.ascontiguousarray(
             np.zeros(0, triangle_dtype) if triangles is None else np.asarray(triangles, dtype=triangle_dtype)
         )
+        self.mtriangles = np.ascontiguousarray(
+            np.zeros(0, mtriangle_dtype) if mtriangles is None else np.asarray(mtriangles, dtype=mtriangle_dtype)
+        )
 
     @property
     def n_objects(self):
-        return len(self.spheres) + len(self.mspheres) + len(self.triangles)
+        return len(self.spheres) + len(self.mspheres) + len(self.triangles) + len(self.mtriangles)
 
     def counts(self):
         return dict(
@@ -106,6 +114,7 @@ class SceneArrays:
             spheres=len(self.spheres),
             mspheres=len(self.mspheres),
             triangles=len(self.triangles),
+            mtriangles=len(self.mtriangles),
         )
 
     # ---- (de)serialisation used by the golden fixtures (tests/golden/*.npz) ----
@@ -116,11 +125,14 @@ class SceneArrays:
             spheres=self.spheres.view(np.uint8),
             mspheres=self.mspheres.view(np.uint8),
             triangles=self.triangles.view(np.uint8),
+            mtriangles=self.mtriangles.view(np.uint8),
         )
 
     @classmethod
     def from_npz_dict(cls, d):
         def v(name, dt):
+            if name not in d:  # fixtures written before a primitive kind existed
+                return np.zeros(0, dt)
             a = np.ascontiguousarray(d[name]).view(np.uint8)
             return a.view(dt) if a.size else np.zeros(0, dt)
 
@@ -130,4 +142,5 @@ class SceneArrays:
             v("spheres", sphere_dtype),
             v("mspheres", msphere_dtype),
             v("triangles", triangle_dtype),
+            v("mtriangles", mtriangle_dtype),
         )

@@ -38,6 +38,7 @@ class _OrcScene(C.Structure):
         ("spheres", C.c_void_p), ("n_spheres", C.c_int),
         ("mspheres", C.c_void_p), ("n_mspheres", C.c_int),
         ("triangles", C.c_void_p), ("n_triangles", C.c_int),
+        ("mtriangles", C.c_void_p), ("n_mtriangles", C.c_int),
     ]
 
 
@@ -95,6 +96,7 @@ class Oracle:
         s.spheres, s.n_spheres = scene.spheres.ctypes.data, len(scene.spheres)
         s.mspheres, s.n_mspheres = scene.mspheres.ctypes.data, len(scene.mspheres)
         s.triangles, s.n_triangles = scene.triangles.ctypes.data, len(scene.triangles)
+        s.mtriangles, s.n_mtriangles = scene.mtriangles.ctypes.data, len(scene.mtriangles)
         self._s = s
         self._bvh = None
 
