@@ -279,6 +279,15 @@ __device__ __forceinline__ void triangle_unit_normal(float ax, float ay, float a
     unit3_rn(nx, ny, nz);
 }
 
+// out of line: only moving triangles recompute their normal at shading time, and the three normalisations would
+// otherwise sit in the middle of every kernel's shading code
+static __device__ __noinline__ float3 triangle_unit_normal_cold(float4 b, float4 c)
+{
+    float3 n;
+    triangle_unit_normal(b.x, b.y, b.z, c.x, c.y, c.z, n.x, n.y, n.z);
+    return n;
+}
+
 // triangle.h:35-75: Moeller-Trumbore, numerators in double, division-free barycentric tests, exclusive range.
 // (v0x, v0y, v0z) is the first vertex in double: the stored one, or v0(time) of a translating instance triangle.
 __device__ __forceinline__ bool triangle_test(const Ray &r, double v0x, double v0y, double v0z, float4 B, float4 C,
@@ -325,7 +334,7 @@ __device__ __forceinline__ bool candidate_wins(float t, int type, int obj, float
 }
 
 // Test leaf `slot` (type known) and update the running closest hit.
-template <bool COUNT>
+template <bool COUNT, bool MTRI = true>
 __device__ __forceinline__ void leaf_test(const float4 *__restrict__ leaves, const int2 *__restrict__ info, int slot,
                                           int type, const Ray &r, const RayPre &p, float t_min, Hit &best,
                                           TravCounters &cnt)
@@ -350,7 +359,7 @@ __device__ __forceinline__ void leaf_test(const float4 *__restrict__ leaves, con
     else {
         float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
         double v0x = a.x, v0y = a.y, v0z = a.z;
-        if (type == PRIM_MTRIANGLE) { // the instance translates: meet the triangle where it is at the ray's time
+        if (MTRI && type == PRIM_MTRIANGLE) { // the instance translates: meet the triangle where it is at the ray's time
             double tm = r.tm;
             v0x = __fma_rn((double)a.w, tm, v0x);
             v0y = __fma_rn((double)b.w, tm, v0y);
@@ -436,12 +445,12 @@ __device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, cons
     }
 }
 
-template <bool COUNT>
+template <bool COUNT, bool MTRI = true>
 __device__ __forceinline__ void leaf_step(const float4 *__restrict__ leaves, const int2 *__restrict__ info, const Ray &r,
                                           const RayPre &p, float t_min, Hit &best, int &cur, int &sp, int *stack,
                                           TravCounters &cnt)
 {
-    leaf_test<COUNT>(leaves, info, (~cur) >> 2, (~cur) & 3, r, p, t_min, best, cnt);
+    leaf_test<COUNT, MTRI>(leaves, info, (~cur) >> 2, (~cur) & 3, r, p, t_min, best, cnt);
     cur = sp > 0 ? stack[--sp] : TRAV_DONE;
 }
 
@@ -470,6 +479,9 @@ struct HitRecord {
     int obj, mat;
 };
 
+// MTRI = false compiles the moving-triangle cases out (the pool kernel picks the variant per scene: the dead
+// branches alone cost 1 % on the headline workload)
+template <bool MTRI = true>
 __device__ __forceinline__ HitRecord hit_record(const float4 *__restrict__ leaves, const int2 *__restrict__ info,
                                                 const Ray &r, const Hit &h)
 {
@@ -485,9 +497,12 @@ __device__ __forceinline__ HitRecord hit_record(const float4 *__restrict__ leave
         rec.ny = b.w;
         rec.nz = c.w;
     }
-    else if (type == PRIM_MTRIANGLE) { // a translation leaves the face normal alone; the record has no room for it
+    else if (MTRI && type == PRIM_MTRIANGLE) { // a translation leaves the face normal alone; the record has no room for it
         float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
-        triangle_unit_normal(b.x, b.y, b.z, c.x, c.y, c.z, rec.nx, rec.ny, rec.nz);
+        float3 n = triangle_unit_normal_cold(b, c);
+        rec.nx = n.x;
+        rec.ny = n.y;
+        rec.nz = n.z;
     }
     else {
         float cx = a.x, cy = a.y, cz = a.z;

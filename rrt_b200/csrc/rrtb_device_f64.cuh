@@ -263,11 +263,10 @@ __device__ __forceinline__ HitRecordD hit_record_d(const float4 *__restrict__ le
     }
     else if (type == PRIM_MTRIANGLE) {
         float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
-        float nx, ny, nz;
-        triangle_unit_normal(b.x, b.y, b.z, c.x, c.y, c.z, nx, ny, nz);
-        rec.nx = (double)nx;
-        rec.ny = (double)ny;
-        rec.nz = (double)nz;
+        float3 n = triangle_unit_normal_cold(b, c);
+        rec.nx = (double)n.x;
+        rec.ny = (double)n.y;
+        rec.nz = (double)n.z;
     }
     else {
         double cx = a.x, cy = a.y, cz = a.z;

@@ -43,7 +43,7 @@ struct WarpPool { // SoA, one per warp, in dynamic shared memory
     unsigned char gq[POOL]; // gen stack
 };
 
-template <bool COUNT_RAYS, int NODE_UNROLL, bool STAGE_TOP>
+template <bool COUNT_RAYS, int NODE_UNROLL, bool STAGE_TOP, bool MTRI = false>
 __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
                     ++rays;
                     ++hits;
                 }
-                HitRecord rec = hit_record(leaves, info, r, h);
+                HitRecord rec = hit_record<MTRI>(leaves, info, r, h);
                 uint4 rnd = philox4x32_10(make_uint4((uint32_t)wp.pixel[sl], (uint32_t)wp.sample[sl], 2u + (uint32_t)bounce, 0u), a.key);
                 float4 m = __ldg(&s.materials[rec.mat]);
                 int mtype = __ldg(&s.material_type[rec.mat]);
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
             if (leaf_mask) {
                 const unsigned node_mask = __ballot_sync(0xffffffffu, cur >= 0);
                 if (__popc(leaf_mask) >= a.th_leaf || node_mask == 0u) {
-                    if (at_leaf) leaf_step<COUNT_RAYS>(leaves, info, ray, pre, 0.001f, best, cur, sp, stack, tc);
+                    if (at_leaf) leaf_step<COUNT_RAYS, MTRI>(leaves, info, ray, pre, 0.001f, best, cur, sp, stack, tc);
                 }
             }
             // lanes whose traversal ended publish the hit and go idle
