@@ -88,12 +88,15 @@ def test_f64_render_bit_exact_vs_oracle(ctx, golden):
     W, H, spp = 96, 64, 6
     orc = Oracle(scene)
     want, fixed, cnt = orc.render_f64(W, H, spp, 50, 1984)
-    for use_bvh in (True, False):
+    # LBVH with the state-machine kernel (default) and the one-segment-per-round kernel, then the flat scan
+    for use_bvh, sched in ((True, 0), (True, 1), (False, 0)):
         ctx.set_scene(scene, use_bvh=use_bvh)
-        img, st = ctx.render(W, H, spp, 50, seed=1984, count_rays=True, dtype=np.float64, precision="f64")
-        assert st["paths"] == W * H * spp == cnt["paths"]
-        assert st["rays"] == cnt["rays"] and st["hits"] == cnt["hits"], (name, use_bvh, st, cnt)
-        assert img.tobytes() == want.tobytes(), (name, use_bvh, float(np.abs(img - want).max()))
+        for count in (True, False):
+            img, st = ctx.render(W, H, spp, 50, seed=1984, count_rays=count, dtype=np.float64, precision="f64", scheduler=sched)
+            assert st["paths"] == W * H * spp == cnt["paths"]
+            if count:
+                assert st["rays"] == cnt["rays"] and st["hits"] == cnt["hits"], (name, use_bvh, sched, st, cnt)
+            assert img.tobytes() == want.tobytes(), (name, use_bvh, sched, count, float(np.abs(img - want).max()))
     # shallow depth cut-offs (rrt.cu:78) too
     ctx.set_scene(scene, use_bvh=True)
     for depth in (1, 3):
