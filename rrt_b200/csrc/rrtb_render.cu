@@ -449,10 +449,7 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
         const bool bvh = ctx->use_bvh != 0, cnt = p->count_rays != 0;
         int rc;
         if (f64) {
-            const bool sm = bvh && p->scheduler != RRTB_SCHED_SIMPLE; // the state machine is the LBVH default
-            if (sm && cnt) rc = launch_persistent(ctx, k_render_f64_sm<true>, a, &blocks);
-            else if (sm) rc = launch_persistent(ctx, k_render_f64_sm<false>, a, &blocks);
-            else if (bvh && cnt) rc = launch_persistent(ctx, k_render_f64<true, true>, a, &blocks);
+            if (bvh && cnt) rc = launch_persistent(ctx, k_render_f64<true, true>, a, &blocks);
             else if (bvh) rc = launch_persistent(ctx, k_render_f64<true, false>, a, &blocks);
             else if (cnt) rc = launch_persistent(ctx, k_render_f64<false, true>, a, &blocks);
             else rc = launch_persistent(ctx, k_render_f64<false, false>, a, &blocks);

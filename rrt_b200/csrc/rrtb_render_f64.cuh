@@ -1,15 +1,8 @@
 // rrtb_render_f64.cuh -- render kernel and test hooks of the DOUBLE integrator (included by
 // rrtb_render.cu).  Replaces, for the reference's `rrtd` build, cuda_render + ray_color (rrt.cu:42-122) with
-// FP_T = double.  Two kernels:
-//   k_render_f64      persistent, one path per lane, the warp reconverges after every segment (flat scan, and the
-//                     RRTB_SCHED_SIMPLE form of the LBVH path)
-//   k_render_f64_sm   the LBVH default: a per-warp STATE MACHINE.  Every lane owns one path in registers and is in
-//                     one of the states START / TRAVERSE / SHADE; the warp votes which phase to run next (node
-//                     visits while enough lanes are at internal nodes, then the double leaf tests, then 32-wide
-//                     shading + ray generation), so the expensive double-precision leaf tests and shading run with
-//                     most lanes active instead of waiting on the warp's slowest traversal (ncu: 11 -> 18 active
-//                     lanes per instruction).  The double path state (ray, throughput, record) does not fit the
-//                     pool scheduler's 64-register / 60-byte-slot budget, hence registers and no pool.
+// FP_T = double.  Scheduling is the persistent one-path-per-lane form of k_render; the double path state (ray,
+// throughput, hit record) does not fit the pool scheduler's 64-register / 60-byte-slot budget, and this is the
+// accuracy build, not the headline one.
 #pragma once
 #include "rrtb_device_f64.cuh"
 
@@ -116,172 +109,6 @@ __global__ void __launch_bounds__(RENDER_TPB, 2) k_render_f64(const RenderArgs a
                     pixel = -1;
                 }
             }
-        }
-    }
-    if (COUNT_RAYS) {
-        unsigned long long v[6] = {rays, tc.box, tc.sph, tc.msph, tc.tri, hits};
-        for (int k = 0; k < 6; ++k) {
-            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-            if (lane == 0 && v[k]) atomicAdd(a.queue + 1 + k, v[k]);
-        }
-    }
-}
-
-// lane states of the state machine
-enum : int { F64_NEED_ITEM = 0, F64_START = 1, F64_TRAVERSE = 2, F64_SHADE = 3, F64_FINISHED = 4 };
-
-template <bool COUNT_RAYS>
-__global__ void __launch_bounds__(RENDER_TPB, 2) k_render_f64_sm(const RenderArgs a)
-{
-    const unsigned lane = threadIdx.x & 31u;
-    const DeviceScene &s = a.scene;
-    const float4 *__restrict__ nodes = s.nodes;
-    const float4 *__restrict__ leaves = s.leaves;
-    const int2 *__restrict__ info = s.leaf_info;
-
-    int st = F64_NEED_ITEM;
-    int pixel = -1, ls = 0, ls_end = 0;
-    unsigned long long acc_r = 0, acc_g = 0, acc_b = 0;
-    RayD ray;
-    double thr_r = 1.0, thr_g = 1.0, thr_b = 1.0;
-    int bounce = 0;
-    RayPre pre;
-    float t_min_f = __double2float_rd(0.001);
-    int cur = TRAV_DONE, sp = 0;
-    int stack[RRTB_STACK];
-    HitD best;
-    best.t = 0.0;
-    best.ref = -1;
-    bool new_path = false; // START: generate a camera ray (else the scattered ray is already in `ray`)
-    unsigned long long rays = 0, hits = 0;
-    TravCounters tc = {0ull, 0ull, 0ull, 0ull};
-
-    while (true) {
-        // ---------------- NODE phase: lanes at internal nodes visit them while enough of them remain
-        if (__ballot_sync(0xffffffffu, st == F64_TRAVERSE && cur >= 0)) {
-            int it = 0;
-            do {
-                if (st == F64_TRAVERSE && cur >= 0)
-                    node_step<COUNT_RAYS>(nodes, pre, t_min_f, __double2float_ru(best.t), cur, sp, stack, tc);
-            } while (++it < a.step_iters && __popc(__ballot_sync(0xffffffffu, st == F64_TRAVERSE && cur >= 0)) >= a.th_node);
-        }
-        // ---------------- LEAF phase: the double primitive tests, once enough lanes wait at a leaf
-        {
-            const bool at_leaf = st == F64_TRAVERSE && cur < 0 && cur != TRAV_DONE;
-            const unsigned leaf_mask = __ballot_sync(0xffffffffu, at_leaf);
-            const unsigned node_mask = __ballot_sync(0xffffffffu, st == F64_TRAVERSE && cur >= 0);
-            if (leaf_mask && (__popc(leaf_mask) >= a.th_leaf || node_mask == 0u)) {
-                if (at_leaf) {
-                    leaf_test_d<COUNT_RAYS>(leaves, info, (~cur) >> 2, (~cur) & 3, ray, 0.001, best, tc);
-                    cur = sp > 0 ? stack[--sp] : TRAV_DONE;
-                }
-            }
-        }
-        if (st == F64_TRAVERSE && cur == TRAV_DONE) st = F64_SHADE;
-
-        // ---------------- SHADE / START phase: when most lanes have finished their segment, or nothing else is left
-        const unsigned trav_mask = __ballot_sync(0xffffffffu, st == F64_TRAVERSE);
-        const unsigned wait_mask = __ballot_sync(0xffffffffu, st == F64_SHADE || st == F64_START || st == F64_NEED_ITEM);
-        if (wait_mask == 0u) {
-            if (trav_mask == 0u) break; // every lane FINISHED
-            continue;
-        }
-        if (__popc(wait_mask) < a.th_fetch && trav_mask != 0u) continue;
-
-        if (st == F64_SHADE) { // rrt.cu:50-76 in double
-            const int sample = a.shard_mode == RRTB_SHARD_SAMPLES ? ls * a.world + a.rank : ls;
-            if (COUNT_RAYS) {
-                ++rays;
-                if (best.ref >= 0) ++hits;
-            }
-            bool path_end = false;
-            double lr = 0.0, lg = 0.0, lb = 0.0;
-            if (best.ref < 0) {
-                sky_d(ray, thr_r, thr_g, thr_b, lr, lg, lb);
-                path_end = true;
-            }
-            else {
-                HitRecordD rec = hit_record_d(leaves, info, ray, best);
-                uint4 rnd = philox4x32_10(make_uint4((uint32_t)pixel, (uint32_t)sample, 2u + (uint32_t)bounce, 0u), a.key);
-                float4 m = __ldg(&s.materials[rec.mat]);
-                int mtype = __ldg(&s.material_type[rec.mat]);
-                double dx, dy, dz, ar, ag, ab;
-                if (scatter_d(mtype, m, ray, rec, rnd, dx, dy, dz, ar, ag, ab)) {
-                    thr_r = __dmul_rn(thr_r, ar);
-                    thr_g = __dmul_rn(thr_g, ag);
-                    thr_b = __dmul_rn(thr_b, ab);
-                    ray.ox = rec.px; ray.oy = rec.py; ray.oz = rec.pz;
-                    ray.dx = dx; ray.dy = dy; ray.dz = dz;
-                    if (++bounce >= a.max_depth) path_end = true; // exceeded depth: black (rrt.cu:78)
-                }
-                else {
-                    path_end = true; // absorbed: black (rrt.cu:61-63)
-                }
-            }
-            st = F64_START;
-            new_path = false;
-            if (path_end) {
-                acc_r += to_fixed_d(lr);
-                acc_g += to_fixed_d(lg);
-                acc_b += to_fixed_d(lb);
-                new_path = true;
-                if (++ls >= ls_end) { // flush the chunk
-                    unsigned long long *dst = a.accum + 3ull * (unsigned long long)pixel;
-                    atomicAdd(dst + 0, acc_r);
-                    atomicAdd(dst + 1, acc_g);
-                    atomicAdd(dst + 2, acc_b);
-                    acc_r = acc_g = acc_b = 0;
-                    pixel = -1;
-                    st = F64_NEED_ITEM;
-                }
-            }
-        }
-        // refill: the work items of k_render: (tile, chunk of CHUNK samples, pixel in tile)
-        {
-            const bool need = st == F64_NEED_ITEM;
-            const unsigned need_mask = __ballot_sync(0xffffffffu, need);
-            if (need_mask) {
-                unsigned long long base = 0;
-                const int leader = __ffs(need_mask) - 1;
-                if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need_mask));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (need) {
-                    unsigned long long item = base + __popc(need_mask & ((1u << lane) - 1u));
-                    if (item >= a.n_items) {
-                        st = F64_FINISHED;
-                    }
-                    else {
-                        unsigned pit = (unsigned)(item & 31ull);
-                        unsigned long long tile_chunk = item >> 5;
-                        int chunk = (int)(tile_chunk % (unsigned long long)a.n_chunks);
-                        int ltile = (int)(tile_chunk / (unsigned long long)a.n_chunks);
-                        int tile = a.shard_mode == RRTB_SHARD_TILES ? ltile * a.world + a.rank : ltile;
-                        int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
-                        int i = tx * 8 + (int)(pit & 7u), j = ty * 4 + (int)(pit >> 3);
-                        if (i < a.W && j < a.H) {
-                            pixel = j * a.W + i;
-                            ls = chunk * CHUNK;
-                            ls_end = min(ls + CHUNK, a.n_local_samples);
-                            new_path = true;
-                            st = F64_START;
-                        } // else: padding pixel of an edge tile; asks again next round
-                    }
-                }
-            }
-        }
-        if (st == F64_START) { // rrt.cu:112-114 + camera.h:31-38, or the scattered ray; then enter the tree
-            if (new_path) {
-                const int sample = a.shard_mode == RRTB_SHARD_SAMPLES ? ls * a.world + a.rank : ls;
-                ray = camera_ray_d(a.cam, a.W, a.H, pixel % a.W, pixel / a.W, sample, a.key);
-                thr_r = thr_g = thr_b = 1.0;
-                bounce = 0;
-            }
-            pre = ray_pre_d(ray);
-            best.t = __longlong_as_double(0x7ff0000000000000ll);
-            best.ref = -1;
-            cur = 0;
-            sp = 0;
-            st = F64_TRAVERSE;
         }
     }
     if (COUNT_RAYS) {
