@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(RENDER_TPB, 2) k_render(const RenderArgs a)
 }
 
 } // namespace rrtb
-#include "rrtb_render_pool.cuh"
 #include "rrtb_render_f64.cuh"
+#include "rrtb_render_pool.cuh"
 namespace rrtb {
 
 __global__ void k_resolve(const unsigned long long *__restrict__ acc, float *__restrict__ out, size_t n)
@@ -373,10 +373,11 @@ static int launch_persistent(rrtb_ctx *ctx, K kernel, const RenderArgs &args, in
     return RRTB_OK;
 }
 
-template <typename K>
+template <class P, typename K>
 static int launch_pool(rrtb_ctx *ctx, K kernel, const RenderArgs &args, int *blocks_out, bool stage_top)
 {
-    const int smem = (int)(sizeof(WarpPool) * POOL_WARPS + (stage_top ? sizeof(float4) * 4 * RRTB_TOP_NODES : 0));
+    constexpr int POOL = P::POOL;
+    const int smem = (int)(sizeof(WarpPoolT<typename P::real, POOL>) * POOL_WARPS + (stage_top ? sizeof(float4) * 4 * RRTB_TOP_NODES : 0));
     RRTB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
     RRTB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RENDER_TPB, smem));
@@ -425,7 +426,7 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     a.n_chunks = (a.n_local_samples + CHUNK - 1) / CHUNK;
     a.n_items = (unsigned long long)a.n_local_tiles * (unsigned long long)a.n_chunks * 32ull;
     const bool f64 = p->precision == RRTB_PRECISION_F64;
-    const bool use_pool = ctx->use_bvh != 0 && p->scheduler != RRTB_SCHED_SIMPLE && !f64;
+    const bool use_pool = ctx->use_bvh != 0 && p->scheduler != RRTB_SCHED_SIMPLE;
     if (use_pool) // the pool scheduler hands out single camera paths: (tile, sample, pixel in tile)
         a.n_items = (unsigned long long)a.n_local_tiles * (unsigned long long)a.n_local_samples * 32ull;
     a.accum = (unsigned long long *)d_accum;
@@ -448,7 +449,11 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     if (a.n_items > 0 && a.max_depth > 0) { // max_depth 0: the bounce loop never runs (rrt.cu:47), the image is black
         const bool bvh = ctx->use_bvh != 0, cnt = p->count_rays != 0;
         int rc;
-        if (f64) {
+        if (f64 && use_pool) { // the pool scheduler over the double path policy
+            if (cnt) rc = launch_pool<PathF64>(ctx, k_render_pool<true, 2, false, true, PathF64>, a, &blocks, false);
+            else rc = launch_pool<PathF64>(ctx, k_render_pool<false, 2, false, true, PathF64>, a, &blocks, false);
+        }
+        else if (f64) {
             if (bvh && cnt) rc = launch_persistent(ctx, k_render_f64<true, true>, a, &blocks);
             else if (bvh) rc = launch_persistent(ctx, k_render_f64<true, false>, a, &blocks);
             else if (cnt) rc = launch_persistent(ctx, k_render_f64<false, true>, a, &blocks);
@@ -458,12 +463,12 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
             bool stage_top = false; // option, see rrtb_render_pool.cuh
             if (const char *e = getenv("RRTB_STAGE_TOP")) stage_top = atoi(e) != 0;
             if (ctx->n_mtriangles > 0) { // scenes with moving triangles get the variant that knows them
-                if (cnt) rc = launch_pool(ctx, k_render_pool<true, 2, false, true>, a, &blocks, false);
-                else rc = launch_pool(ctx, k_render_pool<false, 2, false, true>, a, &blocks, false);
+                if (cnt) rc = launch_pool<PathF32>(ctx, k_render_pool<true, 2, false, true>, a, &blocks, false);
+                else rc = launch_pool<PathF32>(ctx, k_render_pool<false, 2, false, true>, a, &blocks, false);
             }
-            else if (cnt) rc = launch_pool(ctx, k_render_pool<true, 2, false>, a, &blocks, false);
-            else if (stage_top) rc = launch_pool(ctx, k_render_pool<false, 2, true>, a, &blocks, true);
-            else rc = launch_pool(ctx, k_render_pool<false, 2, false>, a, &blocks, false);
+            else if (cnt) rc = launch_pool<PathF32>(ctx, k_render_pool<true, 2, false>, a, &blocks, false);
+            else if (stage_top) rc = launch_pool<PathF32>(ctx, k_render_pool<false, 2, true>, a, &blocks, true);
+            else rc = launch_pool<PathF32>(ctx, k_render_pool<false, 2, false>, a, &blocks, false);
         }
         else if (bvh && cnt) rc = launch_render_t<true, true>(ctx, a, &blocks);
         else if (bvh) rc = launch_render_t<true, false>(ctx, a, &blocks);

@@ -24,28 +24,142 @@
 // batch the hit/miss branches serialised at ~15 lanes).  Lanes in the middle of a traversal keep their
 // traversal registers across a batch and resume.  Nothing but the per-path radiance leaves the SM.
 // Everything is keyed by (pixel, sample, bounce), so the image is bit-identical to the other schedulers.
+//
+// The kernel is written once over a PATH POLICY: PathF32 is the float integrator (the headline build, 64 registers,
+// 4 blocks/SM, 60-byte slots), PathF64 the double integrator of rrtb_device_f64.cuh (double ray /
+// throughput / hit distance in the slot, 107-byte slots, 2 blocks/SM).  The policy only names types and forwards to
+// the device functions of the two integrators; the scheduler is the same code.
 #pragma once
+#include "rrtb_device_f64.cuh"
 
 namespace rrtb {
 
-static constexpr int POOL = 96;                // path slots per warp
 static constexpr int POOL_WARPS = RENDER_TPB / 32;
 static constexpr int SLOT_FRESH = -2;          // hit_ref marker: nothing to accumulate for this slot
 
-struct WarpPool { // SoA, one per warp, in dynamic shared memory
-    float ox[POOL], oy[POOL], oz[POOL], dx[POOL], dy[POOL], dz[POOL], tm[POOL];
-    float tr[POOL], tg[POOL], tb[POOL];
+template <typename real, int POOL>
+struct WarpPoolT { // SoA, one per warp, in dynamic shared memory
+    real ox[POOL], oy[POOL], oz[POOL], dx[POOL], dy[POOL], dz[POOL], tm[POOL];
+    real tr[POOL], tg[POOL], tb[POOL];
+    real hit_t[POOL];
     int pixel[POOL], sample[POOL], bounce[POOL];
-    float hit_t[POOL];
     int hit_ref[POOL];
     unsigned char tq[POOL]; // trace stack
     unsigned char sq[POOL]; // scatter stack
     unsigned char gq[POOL]; // gen stack
 };
 
-template <bool COUNT_RAYS, int NODE_UNROLL, bool STAGE_TOP, bool MTRI = false>
-__global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs a)
+struct PathF32 { // the float integrator (rrtb_device.cuh)
+    typedef float real;
+    typedef Ray RayT;
+    typedef Hit HitT;
+    typedef HitRecord RecT;
+    static constexpr int POOL = 96;         // path slots per warp
+    static constexpr int BLOCKS_PER_SM = 4; // 64 registers
+    static __device__ __forceinline__ RayPre pre(const Ray &r) { return ray_pre(r); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ float t_min_f() { return 0.001f; }
+    static __device__ __forceinline__ float t_max_f(const Hit &h) { return h.t; }
+    static __device__ __forceinline__ Hit make_hit(float t, int ref)
+    {
+        Hit h;
+        h.t = t;
+        h.ref = ref;
+        h.obj = -1;
+        return h;
+    }
+    template <bool COUNT, bool MTRI>
+    static __device__ __forceinline__ void leaf(const float4 *__restrict__ leaves, const int2 *__restrict__ info, const Ray &r,
+                                                const RayPre &p, Hit &best, int &cur, int &sp, int *stack, TravCounters &tc)
+    {
+        leaf_step<COUNT, MTRI>(leaves, info, r, p, 0.001f, best, cur, sp, stack, tc);
+    }
+    template <bool MTRI>
+    static __device__ __forceinline__ HitRecord record(const float4 *__restrict__ leaves, const int2 *__restrict__ info,
+                                                       const Ray &r, const Hit &h)
+    {
+        return hit_record<MTRI>(leaves, info, r, h);
+    }
+    static __device__ __forceinline__ bool bounce(int mtype, float4 m, const Ray &r, const HitRecord &rec, uint4 rnd, float &dx,
+                                                  float &dy, float &dz, float &ar, float &ag, float &ab)
+    {
+        return scatter(mtype, m, r, rec, rnd, dx, dy, dz, ar, ag, ab);
+    }
+    static __device__ __forceinline__ float mul(float x, float y) { return x * y; }
+    // sky x throughput -> fixed point (rrt.cu:68-75)
+    static __device__ __forceinline__ void sky_fixed(const Ray &r, float tr, float tg, float tb, unsigned long long &fr,
+                                                     unsigned long long &fg, unsigned long long &fb)
+    {
+        float cr, cg, cb;
+        sky(r, cr, cg, cb);
+        fr = to_fixed(tr * cr);
+        fg = to_fixed(tg * cg);
+        fb = to_fixed(tb * cb);
+    }
+    static __device__ __forceinline__ Ray camera(const DeviceCamera &cam, int W, int H, int i, int j, int sample, uint2 key)
+    {
+        return camera_ray(cam, W, H, i, j, sample, key);
+    }
+};
+
+struct PathF64 { // the double integrator (rrtb_device_f64.cuh); bit-exact against oracle/rrt_oracle_f64.c
+    typedef double real;
+    typedef RayD RayT;
+    typedef HitD HitT;
+    typedef HitRecordD RecT;
+    static constexpr int POOL = 96;
+    static constexpr int BLOCKS_PER_SM = 2; // <= 128 registers, 82 KB of slots per block
+    static __device__ __forceinline__ RayPre pre(const RayD &r) { return ray_pre_d(r); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000ll); }
+    static __device__ __forceinline__ float t_min_f() { return __double2float_rd(0.001); }
+    static __device__ __forceinline__ float t_max_f(const HitD &h) { return __double2float_ru(h.t); }
+    static __device__ __forceinline__ HitD make_hit(double t, int ref)
+    {
+        HitD h;
+        h.t = t;
+        h.ref = ref;
+        return h;
+    }
+    template <bool COUNT, bool MTRI>
+    static __device__ __forceinline__ void leaf(const float4 *__restrict__ leaves, const int2 *__restrict__ info, const RayD &r,
+                                                const RayPre &, HitD &best, int &cur, int &sp, int *stack, TravCounters &tc)
+    {
+        leaf_test_d<COUNT>(leaves, info, (~cur) >> 2, (~cur) & 3, r, 0.001, best, tc);
+        cur = sp > 0 ? stack[--sp] : TRAV_DONE;
+    }
+    template <bool MTRI>
+    static __device__ __forceinline__ HitRecordD record(const float4 *__restrict__ leaves, const int2 *__restrict__ info,
+                                                        const RayD &r, const HitD &h)
+    {
+        return hit_record_d(leaves, info, r, h);
+    }
+    static __device__ __forceinline__ bool bounce(int mtype, float4 m, const RayD &r, const HitRecordD &rec, uint4 rnd, double &dx,
+                                                  double &dy, double &dz, double &ar, double &ag, double &ab)
+    {
+        return scatter_d(mtype, m, r, rec, rnd, dx, dy, dz, ar, ag, ab);
+    }
+    static __device__ __forceinline__ double mul(double x, double y) { return __dmul_rn(x, y); }
+    static __device__ __forceinline__ void sky_fixed(const RayD &r, double tr, double tg, double tb, unsigned long long &fr,
+                                                     unsigned long long &fg, unsigned long long &fb)
+    {
+        double lr, lg, lb;
+        sky_d(r, tr, tg, tb, lr, lg, lb);
+        fr = to_fixed_d(lr);
+        fg = to_fixed_d(lg);
+        fb = to_fixed_d(lb);
+    }
+    static __device__ __forceinline__ RayD camera(const DeviceCamera &cam, int W, int H, int i, int j, int sample, uint2 key)
+    {
+        return camera_ray_d(cam, W, H, i, j, sample, key);
+    }
+};
+
+template <bool COUNT_RAYS, int NODE_UNROLL, bool STAGE_TOP, bool MTRI = false, class P = PathF32>
+__global__ void __launch_bounds__(RENDER_TPB, P::BLOCKS_PER_SM) k_render_pool(const RenderArgs a)
 {
+    typedef typename P::real real;
+    typedef WarpPoolT<real, P::POOL> WarpPool;
+    constexpr int POOL = P::POOL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpPool &wp = reinterpret_cast<WarpPool *>(smem_raw)[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
@@ -77,14 +191,11 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
 
     // lane state: the traversal in flight (slot < 0: idle, and then cur == TRAV_DONE)
     int slot = -1;
-    Ray ray;
+    typename P::RayT ray;
     RayPre pre;
     int cur = TRAV_DONE, sp = 0;
     int stack[RRTB_STACK];
-    Hit best;
-    best.t = 0.f;
-    best.ref = -1;
-    best.obj = -1;
+    typename P::HitT best = P::make_hit((real)0, -1);
     bool queue_empty = false; // the global work queue has run dry (warp-uniform)
     unsigned long long rays = 0, hits = 0;
     TravCounters tc = {0ull, 0ull, 0ull, 0ull};
@@ -105,8 +216,8 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
                 ray.ox = wp.ox[slot]; ray.oy = wp.oy[slot]; ray.oz = wp.oz[slot];
                 ray.dx = wp.dx[slot]; ray.dy = wp.dy[slot]; ray.dz = wp.dz[slot];
                 ray.tm = wp.tm[slot];
-                pre = ray_pre(ray);
-                best.t = __int_as_float(0x7f800000);
+                pre = P::pre(ray);
+                best.t = P::inf();
                 best.ref = -1;
                 cur = root;
                 sp = 0;
@@ -122,28 +233,25 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
             __syncwarp(); // every lane has read its slot id before the stacks are pushed to below
             bool to_trace = false, ended = false;
             if (mine) {
-                Ray r;
+                typename P::RayT r;
                 r.ox = wp.ox[sl]; r.oy = wp.oy[sl]; r.oz = wp.oz[sl];
                 r.dx = wp.dx[sl]; r.dy = wp.dy[sl]; r.dz = wp.dz[sl];
                 r.tm = wp.tm[sl];
                 const int bounce = wp.bounce[sl];
-                Hit h;
-                h.t = wp.hit_t[sl];
-                h.ref = wp.hit_ref[sl];
-                h.obj = -1;
+                const typename P::HitT h = P::make_hit(wp.hit_t[sl], wp.hit_ref[sl]);
                 if (COUNT_RAYS) {
                     ++rays;
                     ++hits;
                 }
-                HitRecord rec = hit_record<MTRI>(leaves, info, r, h);
+                typename P::RecT rec = P::template record<MTRI>(leaves, info, r, h);
                 uint4 rnd = philox4x32_10(make_uint4((uint32_t)wp.pixel[sl], (uint32_t)wp.sample[sl], 2u + (uint32_t)bounce, 0u), a.key);
                 float4 m = __ldg(&s.materials[rec.mat]);
                 int mtype = __ldg(&s.material_type[rec.mat]);
-                float dx, dy, dz, ar, ag, ab;
-                if (scatter(mtype, m, r, rec, rnd, dx, dy, dz, ar, ag, ab) && bounce + 1 < a.max_depth) {
+                real dx, dy, dz, ar, ag, ab;
+                if (P::bounce(mtype, m, r, rec, rnd, dx, dy, dz, ar, ag, ab) && bounce + 1 < a.max_depth) {
                     wp.ox[sl] = rec.px; wp.oy[sl] = rec.py; wp.oz[sl] = rec.pz;
                     wp.dx[sl] = dx; wp.dy[sl] = dy; wp.dz[sl] = dz;
-                    wp.tr[sl] *= ar; wp.tg[sl] *= ag; wp.tb[sl] *= ab;
+                    wp.tr[sl] = P::mul(wp.tr[sl], ar); wp.tg[sl] = P::mul(wp.tg[sl], ag); wp.tb[sl] = P::mul(wp.tb[sl], ab);
                     wp.bounce[sl] = bounce + 1;
                     to_trace = true;
                 }
@@ -170,14 +278,14 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
             __syncwarp();
             if (mine && wp.hit_ref[sl] == -1) { // the segment left the scene: sky x throughput (rrt.cu:68-75)
                 if (COUNT_RAYS) ++rays;
-                Ray r;
+                typename P::RayT r;
                 r.dx = wp.dx[sl]; r.dy = wp.dy[sl]; r.dz = wp.dz[sl];
-                float cr, cg, cb;
-                sky(r, cr, cg, cb);
+                unsigned long long fr, fg, fb;
+                P::sky_fixed(r, wp.tr[sl], wp.tg[sl], wp.tb[sl], fr, fg, fb);
                 unsigned long long *dst = a.accum + 3ull * (unsigned long long)wp.pixel[sl];
-                atomicAdd(dst + 0, to_fixed(wp.tr[sl] * cr));
-                atomicAdd(dst + 1, to_fixed(wp.tg[sl] * cg));
-                atomicAdd(dst + 2, to_fixed(wp.tb[sl] * cb));
+                atomicAdd(dst + 0, fr);
+                atomicAdd(dst + 1, fg);
+                atomicAdd(dst + 2, fb);
             }
             // next camera paths: one warp-aggregated atomic on the global queue
             bool to_trace = false;
@@ -219,11 +327,11 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
                     const int i = tx * 8 + (int)(pit & 7u), j = ty * 4 + (int)(pit >> 3);
                     if (i < a.W && j < a.H) { // else: padding pixel of an edge tile, the slot asks again
                         const int sample = a.shard_mode == RRTB_SHARD_SAMPLES ? ls * a.world + a.rank : ls;
-                        Ray r = camera_ray(a.cam, a.W, a.H, i, j, sample, a.key); // rrt.cu:112-114, camera.h:31-38
+                        typename P::RayT r = P::camera(a.cam, a.W, a.H, i, j, sample, a.key); // rrt.cu:112-114, camera.h:31-38
                         wp.ox[sl] = r.ox; wp.oy[sl] = r.oy; wp.oz[sl] = r.oz;
                         wp.dx[sl] = r.dx; wp.dy[sl] = r.dy; wp.dz[sl] = r.dz;
                         wp.tm[sl] = r.tm;
-                        wp.tr[sl] = 1.f; wp.tg[sl] = 1.f; wp.tb[sl] = 1.f;
+                        wp.tr[sl] = (real)1; wp.tg[sl] = (real)1; wp.tb[sl] = (real)1;
                         RRTB_CHECK(sl >= 0 && sl < POOL && j * a.W + i < a.W * a.H);
                         wp.pixel[sl] = j * a.W + i;
                         wp.sample[sl] = sample;
@@ -255,14 +363,14 @@ __global__ void __launch_bounds__(RENDER_TPB, 4) k_render_pool(const RenderArgs 
             do {
 #pragma unroll
                 for (int u = 0; u < NODE_UNROLL; ++u) // node visits between two continue-votes
-                    if (cur >= 0) node_step<COUNT_RAYS, STAGE_TOP>(nodes, pre, 0.001f, best.t, cur, sp, stack, tc, top);
+                    if (cur >= 0) node_step<COUNT_RAYS, STAGE_TOP>(nodes, pre, P::t_min_f(), P::t_max_f(best), cur, sp, stack, tc, top);
             } while (++it < a.step_iters && __popc(__ballot_sync(0xffffffffu, cur >= 0)) >= a.th_node);
             const bool at_leaf = cur < 0 && cur != TRAV_DONE;
             const unsigned leaf_mask = __ballot_sync(0xffffffffu, at_leaf);
             if (leaf_mask) {
                 const unsigned node_mask = __ballot_sync(0xffffffffu, cur >= 0);
                 if (__popc(leaf_mask) >= a.th_leaf || node_mask == 0u) {
-                    if (at_leaf) leaf_step<COUNT_RAYS, MTRI>(leaves, info, ray, pre, 0.001f, best, cur, sp, stack, tc);
+                    if (at_leaf) P::template leaf<COUNT_RAYS, MTRI>(leaves, info, ray, pre, best, cur, sp, stack, tc);
                 }
             }
             // lanes whose traversal ended publish the hit and go idle
