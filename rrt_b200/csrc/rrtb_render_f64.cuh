@@ -1,8 +1,7 @@
 // rrtb_render_f64.cuh -- render kernel and test hooks of the DOUBLE integrator (included by
 // rrtb_render.cu).  Replaces, for the reference's `rrtd` build, cuda_render + ray_color (rrt.cu:42-122) with
-// FP_T = double.  Scheduling is the persistent one-path-per-lane form of k_render; the double path state (ray,
-// throughput, hit record) does not fit the pool scheduler's 64-register / 60-byte-slot budget, and this is the
-// accuracy build, not the headline one.
+// FP_T = double.  k_render_f64 is the persistent one-path-per-lane form (flat scan, and RRTB_SCHED_SIMPLE); the LBVH
+// default is the pool scheduler of rrtb_render_pool.cuh instantiated over the PathF64 policy (final.txt: 1.8x).
 #pragma once
 #include "rrtb_device_f64.cuh"
 

@@ -27,7 +27,7 @@
 //
 // The kernel is written once over a PATH POLICY: PathF32 is the float integrator (the headline build, 64 registers,
 // 4 blocks/SM, 60-byte slots), PathF64 the double integrator of rrtb_device_f64.cuh (double ray /
-// throughput / hit distance in the slot, 107-byte slots, 2 blocks/SM).  The policy only names types and forwards to
+// throughput / hit distance in the slot, 107-byte slots, 3 blocks/SM).  The policy only names types and forwards to
 // the device functions of the two integrators; the scheduler is the same code.
 #pragma once
 #include "rrtb_device_f64.cuh"
@@ -107,8 +107,10 @@ struct PathF64 { // the double integrator (rrtb_device_f64.cuh); bit-exact again
     typedef RayD RayT;
     typedef HitD HitT;
     typedef HitRecordD RecT;
-    static constexpr int POOL = 96;
-    static constexpr int BLOCKS_PER_SM = 2; // <= 128 registers, 82 KB of slots per block
+    // measured on final.txt / synthetic (ms at 64 / 8 spp): POOL x blocks 96x2 15.7 / 44.1, 128x2 17.6 / 48.6,
+    // 80x3 15.2 / 38.0, 72x3 14.1 / 36.7, 64x3 14.0 / 37.4, 56x3 14.6 / 40.7, 48x3 15.3 / 45.2, 48x4 15.5 / 44.2
+    static constexpr int POOL = 64;
+    static constexpr int BLOCKS_PER_SM = 3; // 80 registers, 55 KB of slots per block
     static __device__ __forceinline__ RayPre pre(const RayD &r) { return ray_pre_d(r); }
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000ll); }
     static __device__ __forceinline__ float t_min_f() { return __double2float_rd(0.001); }
