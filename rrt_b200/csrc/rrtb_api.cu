@@ -210,7 +210,7 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     if ((rc = dev_alloc(ctx, ctx->d_leaves, (size_t)3 * n))) return rc;
     if ((rc = dev_alloc(ctx, ctx->d_leaf_info, (size_t)n))) return rc;
     if ((rc = dev_alloc(ctx, ctx->d_reduce, (size_t)nb * 7 + 16))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_hist, (size_t)256 * n_seg))) return rc;
+    if ((rc = dev_alloc(ctx, ctx->d_hist, (size_t)256 * n_seg + (size_t)(256 * n_seg + 4095) / 4096 + 1))) return rc; // + chunk sums
 
     // materials -> (albedo.xyz, param) + type
     std::vector<float4> mats((size_t)n_materials);

@@ -249,7 +249,66 @@ __global__ void __launch_bounds__(TPB) k_hist(const uint64_t *__restrict__ keys,
     }
 }
 
-// exclusive scan of hist[256 * n_seg] (digit-major), single block
+// Exclusive scan of hist[256 * n_seg] (digit-major) in three grid-wide steps: per-chunk sums, a scan of the chunk
+// sums (one block; <= a few hundred values for a million primitives), per-chunk exclusive scans offset by them.
+// (One block walking the whole array took 0.23 ms per pass at 1.1 M primitives -- over half of the build.)
+static constexpr int SCAN_CHUNK = 4096; // entries per block: 256 threads x 16
+
+__device__ __forceinline__ unsigned int block_exclusive_scan_256(unsigned int v, unsigned int *warp_sums, unsigned int &total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned int incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        unsigned int s = lane < TPB / 32 ? warp_sums[lane] : 0u;
+        unsigned int si = s;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += t;
+        }
+        if (lane < TPB / 32) warp_sums[lane] = si - s; // exclusive prefix of the warp sums
+        if (lane == 31) warp_sums[TPB / 32] = si;       // block total
+    }
+    __syncthreads();
+    total = warp_sums[TPB / 32];
+    return warp_sums[w] + incl - v;
+}
+
+__global__ void __launch_bounds__(TPB) k_scan_sums(const unsigned int *__restrict__ hist, int total, unsigned int *__restrict__ sums)
+{
+    __shared__ unsigned int warp_sums[TPB / 32 + 1];
+    const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * 16;
+    unsigned int v = 0;
+    for (int k = 0; k < 16; ++k)
+        if (base + k < total) v += hist[base + k];
+    unsigned int tot;
+    block_exclusive_scan_256(v, warp_sums, tot);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(TPB) k_scan_apply(unsigned int *__restrict__ hist, int total, const unsigned int *__restrict__ sums)
+{
+    __shared__ unsigned int warp_sums[TPB / 32 + 1];
+    const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * 16;
+    unsigned int x[16], v = 0;
+    for (int k = 0; k < 16; ++k) {
+        x[k] = base + k < total ? hist[base + k] : 0u;
+        v += x[k];
+    }
+    unsigned int tot;
+    unsigned int run = sums[blockIdx.x] + block_exclusive_scan_256(v, warp_sums, tot);
+    for (int k = 0; k < 16; ++k) {
+        if (base + k < total) hist[base + k] = run;
+        run += x[k];
+    }
+}
+
+// exclusive scan of a short array in place, single block (the chunk sums)
 __global__ void __launch_bounds__(1024) k_scan(unsigned int *__restrict__ hist, int total)
 {
     __shared__ unsigned int warp_sums[32];
@@ -515,7 +574,11 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 32 + 8 * pass;
         k_hist<<<sort_blocks, TPB, 0, st>>>(src, n, shift, n_seg, ctx->d_hist);
-        k_scan<<<1, 1024, 0, st>>>(ctx->d_hist, 256 * n_seg);
+        const int hist_len = 256 * n_seg, scan_blocks = (hist_len + SCAN_CHUNK - 1) / SCAN_CHUNK;
+        unsigned int *sums = ctx->d_hist + hist_len; // scan_blocks entries behind the histogram
+        k_scan_sums<<<scan_blocks, TPB, 0, st>>>(ctx->d_hist, hist_len, sums);
+        k_scan<<<1, 1024, 0, st>>>(sums, scan_blocks);
+        k_scan_apply<<<scan_blocks, TPB, 0, st>>>(ctx->d_hist, hist_len, sums);
         k_scatter<<<sort_blocks, TPB, 0, st>>>(src, dst, n, shift, n_seg, ctx->d_hist);
         uint64_t *t = src;
         src = dst;
@@ -540,9 +603,20 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
                                          ctx->d_node_box, bc, ctx->d_nodes);
     k_flatten_leaves<<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_prim, ctx->d_prim_info, ctx->d_leaves,
                                          ctx->d_leaf_info);
-    k_build_top<<<1, 32, 0, st>>>(ctx->d_nodes, max(n - 1, 1), ctx->d_top_nodes, ctx->d_n_top);
     RRTB_CUDA(ctx, cudaGetLastError());
-    RRTB_CUDA(ctx, cudaMemcpyAsync(&ctx->n_top, ctx->d_n_top, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ctx->n_top = 0; // the breadth-first top copy is built on demand (build_top)
+    return RRTB_OK;
+}
+
+// The staged top of the tree is an option of the pool kernel (off by default, rrtb_render_pool.cuh), so its
+// single-thread builder (0.3 ms) runs only for a render that asks for it.
+int build_top(rrtb_ctx *ctx)
+{
+    if (ctx->n_top > 0) return RRTB_OK;
+    k_build_top<<<1, 32, 0, ctx->stream>>>(ctx->d_nodes, max(ctx->n_prims - 1, 1), ctx->d_top_nodes, ctx->d_n_top);
+    RRTB_CUDA(ctx, cudaGetLastError());
+    RRTB_CUDA(ctx, cudaMemcpyAsync(&ctx->n_top, ctx->d_n_top, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RRTB_OK;
 }
 

@@ -68,6 +68,7 @@ int cuda_fail(rrtb_ctx *ctx, cudaError_t e, const char *expr, const char *file, 
 
 // rrtb_bvh.cu
 void free_scene(rrtb_ctx *ctx);
+int build_top(rrtb_ctx *ctx); // breadth-first copy of the top of the tree, on demand (RRTB_STAGE_TOP)
 
 // rrtb_render.cu
 DeviceScene device_scene(const rrtb_ctx *ctx);

@@ -462,6 +462,7 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
         else if (use_pool) {
             bool stage_top = false; // option, see rrtb_render_pool.cuh
             if (const char *e = getenv("RRTB_STAGE_TOP")) stage_top = atoi(e) != 0;
+            if (stage_top && (rc = build_top(ctx))) return rc;
             if (ctx->n_mtriangles > 0) { // scenes with moving triangles get the variant that knows them
                 if (cnt) rc = launch_pool<PathF32>(ctx, k_render_pool<true, 2, false, true>, a, &blocks, false);
                 else rc = launch_pool<PathF32>(ctx, k_render_pool<false, 2, false, true>, a, &blocks, false);
