@@ -250,6 +250,7 @@ for name in ("final", "test2", "test3"):
     ctx.set_scene(scene, True)
     for sched in (1, 2):
         render(70, 45, 6, 50, 7, scheduler=sched, count_rays=True)
+        render(70, 45, 3, 50, 7, scheduler=sched, precision="f64")  # the double integrator on both schedulers
     render(33, 17, 4, 50, 7, 1, 3, 1)
 write_synthetic_scene("/tmp/_dbg_synth.txt", n_spheres=1500, ico_level=2, grid=3)
 ctx.set_scene(Scene.from_file("/tmp/_dbg_synth.txt", 64, 36), True)
