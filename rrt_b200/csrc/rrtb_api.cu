@@ -164,7 +164,7 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     if (n_spheres < 0 || n_mspheres < 0 || n_triangles < 0) return invalid(ctx, "negative primitive count");
     const long long n_ll = (long long)n_spheres + n_mspheres + n_triangles + n_mtriangles;
     if (n_ll <= 0) return invalid(ctx, "scene has no objects");
-    if (n_ll >= (1ll << 29)) return invalid(ctx, "too many primitives (limit 2^29)");
+    if (n_ll >= (1ll << 28)) return invalid(ctx, "too many primitives (limit 2^28: 32-bit element offsets such as 6 * id)");
     if ((n_spheres && !spheres) || (n_mspheres && !mspheres) || (n_triangles && !triangles))
         return invalid(ctx, "null primitive array");
     const int n = (int)n_ll;

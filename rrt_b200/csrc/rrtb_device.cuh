@@ -405,7 +405,7 @@ __device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, 
 #define RRTB_STACK 64
 #define TRAV_DONE ((int)0x80000000)
 // internal-node refs with this bit set index the breadth-first "top" copy of the tree that the pool kernel
-// stages in shared memory (node counts are < 2^29, so bit 30 is free)
+// stages in shared memory (node counts are < 2^28, so bit 30 is free)
 #define TOP_FLAG 0x40000000
 #define RRTB_TOP_NODES 112
 
