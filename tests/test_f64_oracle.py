@@ -50,6 +50,24 @@ def test_f64_primary_hits_match_reference_double(live):
     assert np.array_equal(rec[m, 6] != 0, r10[m, 7] != 0)
 
 
+def test_f64_primary_hits_match_reference_fixture(golden):
+    """The committed fixtures (tests/golden, produced by the reference's double build, tools/make_golden.py) pin the
+    double oracle wherever oracle/_ref is absent: ids identical, t and the hit point within 1e-9, normals of spheres
+    within 1e-9 and of triangles within the float rounding of the stored normal."""
+    name, scene, d = golden
+    orc = Oracle(scene)
+    rays = d["rays"].astype(np.float64)
+    hit = d["ref_id"] >= 0
+    for mode in ("scan", "bvh"):
+        ids, t, rec = orc.trace_f64(rays, 0.001, mode, want_rec=True)
+        assert np.array_equal(ids, d["ref_id"]), (name, mode, int((ids != d["ref_id"]).sum()))
+        rel = np.abs(t[hit] - d["ref_t"][hit]) / np.abs(d["ref_t"][hit])
+        assert rel.max() <= 1e-9, (name, mode, rel.max())
+        assert np.allclose(rec[hit, 0:3], d["ref_rec"][hit, 1:4], rtol=1e-9, atol=1e-9)
+        assert np.allclose(rec[hit, 3:6], d["ref_rec"][hit, 4:7], rtol=0, atol=2e-6)
+        assert np.array_equal(rec[hit, 6] != 0, d["ref_rec"][hit, 7] != 0)
+
+
 def test_f64_agrees_with_float_oracle():
     """The two integrators see the same scene: ids equal, t within the float policy's 2.2e-6."""
     from rrt_b200.synthetic import synthetic_scene_text
