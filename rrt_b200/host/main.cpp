@@ -75,8 +75,12 @@ static bool same_geometry(const rrtb_scene *a, const rrtb_scene *b)
     rrtb_scene_counts(b, cb);
     for (int k = 0; k < 4; ++k)
         if (ca[k] != cb[k]) return false;
+    const int nmt = rrtb_scene_mtriangle_count(a);
+    if (nmt != rrtb_scene_mtriangle_count(b)) return false;
     const rrtb_camera *cam_a = rrtb_scene_camera(a), *cam_b = rrtb_scene_camera(b);
-    if (ca[2] > 0 && (cam_a->time0 != cam_b->time0 || cam_a->time1 != cam_b->time1)) return false; // moving-sphere boxes span the shutter
+    // boxes of moving spheres / moving triangles span the shutter
+    if (ca[2] + nmt > 0 && (cam_a->time0 != cam_b->time0 || cam_a->time1 != cam_b->time1)) return false;
+    if (nmt > 0 && memcmp(rrtb_scene_mtriangles(a), rrtb_scene_mtriangles(b), sizeof(rrtb_mtriangle) * nmt) != 0) return false;
     return memcmp(rrtb_scene_materials(a), rrtb_scene_materials(b), sizeof(rrtb_material) * ca[0]) == 0 &&
            (ca[1] == 0 || memcmp(rrtb_scene_spheres(a), rrtb_scene_spheres(b), sizeof(rrtb_sphere) * ca[1]) == 0) &&
            (ca[2] == 0 || memcmp(rrtb_scene_mspheres(a), rrtb_scene_mspheres(b), sizeof(rrtb_msphere) * ca[2]) == 0) &&
