@@ -409,6 +409,14 @@ __device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, 
 #define TOP_FLAG 0x40000000
 #define RRTB_TOP_NODES 112
 
+// 32-byte read-only load (PTX ISA 8.8 ld.global.nc.v8.f32, SASS LDG.E.256.CONSTANT; p must be 32-byte aligned)
+__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b)
+{
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+
 // TOP = true: refs carrying TOP_FLAG are fetched from `top` (shared memory), the others from `nodes` (global)
 template <bool COUNT, bool TOP = false>
 __device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, const RayPre &p, float t_min, float t_max,
@@ -420,8 +428,8 @@ __device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, cons
         n0 = q[0]; n1 = q[1]; n2 = q[2]; n3 = q[3];
     }
     else {
-        n0 = __ldg(nodes + 4 * cur); n1 = __ldg(nodes + 4 * cur + 1); n2 = __ldg(nodes + 4 * cur + 2);
-        n3 = __ldg(nodes + 4 * cur + 3);
+        ldg256(nodes + 4 * cur, n0, n1); // sm_100a 256-bit loads: a 64-byte node is two LDG.E.256, not four LDG.E.128
+        ldg256(nodes + 4 * cur + 2, n2, n3);
     }
     float tl, tr;
     if (COUNT) cnt.box += 2;
