@@ -470,9 +470,9 @@ __global__ void __launch_bounds__(TPB) k_flatten_nodes(const uint64_t *__restric
             float c[3], h[3];
             for (int k = 0; k < 3; ++k) center_half(b[k], b[3 + k], pad, c[k], h[k]);
             int enc = ~((0 << 2) | prim_type(0, ns, nms, nt));
-            nodes[0] = make_float4(c[0], c[1], c[2], h[0]);
-            nodes[1] = make_float4(h[1], h[2], c[0], c[1]);
-            nodes[2] = make_float4(c[2], h[0], h[1], h[2]);
+            nodes[0] = make_float4(c[0], c[0], c[1], c[1]);
+            nodes[1] = make_float4(c[2], c[2], h[0], h[0]);
+            nodes[2] = make_float4(h[1], h[1], h[2], h[2]);
             nodes[3] = make_float4(__int_as_float(enc), __int_as_float(enc), 0.f, 0.f);
         }
         return;
@@ -495,9 +495,10 @@ __global__ void __launch_bounds__(TPB) k_flatten_nodes(const uint64_t *__restric
         }
         for (int k = 0; k < 3; ++k) center_half(b[k], b[3 + k], pad, bx[c][k], bx[c][3 + k]);
     }
-    nodes[4 * i + 0] = make_float4(bx[0][0], bx[0][1], bx[0][2], bx[0][3]);
-    nodes[4 * i + 1] = make_float4(bx[0][4], bx[0][5], bx[1][0], bx[1][1]);
-    nodes[4 * i + 2] = make_float4(bx[1][2], bx[1][3], bx[1][4], bx[1][5]);
+    // children interleaved per component (rrtb_device.cuh "BVH node"): one FFMA2 serves both boxes
+    nodes[4 * i + 0] = make_float4(bx[0][0], bx[1][0], bx[0][1], bx[1][1]);
+    nodes[4 * i + 1] = make_float4(bx[0][2], bx[1][2], bx[0][3], bx[1][3]);
+    nodes[4 * i + 2] = make_float4(bx[0][4], bx[1][4], bx[0][5], bx[1][5]);
     nodes[4 * i + 3] = make_float4(__int_as_float(enc[0]), __int_as_float(enc[1]), 0.f, 0.f);
 }
 

@@ -43,9 +43,10 @@ __device__ unsigned int g_rrtb_violations;
 //   moving tri.    a = (base.xyz, rate.x) b = (e1.xyz, rate.y) c = (e2.xyz, rate.z)   v0(time) = fma(rate, time, base)
 //                  (include/rrtb.h "rrtb_mtriangle"; the normal is recomputed at shading time)
 // leaf_info[k] = (object id, material index)
-// BVH node: 4 x float4 (64 B): padded boxes of both children + child refs
-//   n0 = (L.c.xyz, L.h.x)  n1 = (L.h.y, L.h.z, R.c.x, R.c.y)  n2 = (R.c.z, R.h.xyz)   c = centre, h = half extent
-//   n3 = (bits(left ref), bits(right ref), -, -)
+// BVH node: 4 x float4 (64 B): padded boxes of both children + child refs, the two children INTERLEAVED per
+// component so that one packed FP32x2 instruction (sm_100a FFMA2) works on the left and the right box at once:
+//   n0 = (L.c.x, R.c.x, L.c.y, R.c.y)  n1 = (L.c.z, R.c.z, L.h.x, R.h.x)  n2 = (L.h.y, R.h.y, L.h.z, R.h.z)
+//   n3 = (bits(left ref), bits(right ref), -, -)                              c = centre, h = half extent
 // child ref >= 0: internal node index;  < 0: leaf, ~ref = (leaf slot << 2) | type
 enum : int { PRIM_SPHERE = 0, PRIM_MSPHERE = 1, PRIM_TRIANGLE = 2, PRIM_MTRIANGLE = 3 };
 
@@ -197,19 +198,51 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
     return r;
 }
 
-// Slab test on one (already padded) box given as centre c and half extent h; inclusive; entry distance in tn.
-// Per axis  t_c = (c - o)/d,  u = h/d  ->  [t_c - |u|, t_c + |u|]:  FFMA + FMUL + 2 FADD(|.|), no min/max to
-// order the two planes.  A box costs 12 fma-pipe ops + 2 FMNMX3 + 2 FMNMX + 1 FSETP on the alu pipe, instead
-// of 6 + 11: ncu showed the alu pipe (half the fma pipe's rate) as the busiest unit of the render kernel.
-__device__ __forceinline__ bool box_hit(float cx, float cy, float cz, float hx, float hy, float hz, const RayPre &p,
-                                        float t_min, float t_max, float &tn)
+// Packed FP32x2 arithmetic (PTX ISA 8.6 fma.rn.f32x2, SASS FFMA2): one instruction, two lanes of a 64-bit register
+// pair; a pair built from one scalar twice costs nothing (ptxas encodes it as a broadcast operand `R.F32`, with
+// |.| and negation as operand modifiers).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
 {
-    float tx = fmaf(cx, p.ix, p.oox), ux = fabsf(hx * p.ix);
-    float ty = fmaf(cy, p.iy, p.ooy), uy = fabsf(hy * p.iy);
-    float tz = fmaf(cz, p.iz, p.ooz), uz = fabsf(hz * p.iz);
-    tn = fmaxf(fmax3(tx - ux, ty - uy, tz - uz), t_min);
-    float tf = fminf(fmin3(tx + ux, ty + uy, tz + uz), t_max);
-    return tn <= tf;
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// Slab test of BOTH children of a node (already padded boxes as centre c and half extent h, interleaved L/R);
+// inclusive; entry distances in tl / tr.  Per axis  t_c = (c - o)/d,  [t_c - h|1/d|, t_c + h|1/d|]: three FFMA2
+// for the two boxes (no min/max to order the planes), then per box 2 FMNMX3 + 2 FMNMX + 1 FSETP.  A node visit
+// costs 9 + 10 arithmetic instructions; the scalar form (FFMA + FMUL + 2 FADD per axis and box) cost 24 + 10,
+// and the min/max form before it 12 + 22 on the alu pipe that ncu showed as the busiest unit.
+__device__ __forceinline__ void box_hit2(const float4 &n0, const float4 &n1, const float4 &n2, const RayPre &p, float t_min,
+                                         float t_max, bool &hl, bool &hr, float &tl, float &tr)
+{
+    const float ax = fabsf(p.ix), ay = fabsf(p.iy), az = fabsf(p.iz);
+    const f32x2 tx = fma2(pack2(n0.x, n0.y), pack2(p.ix, p.ix), pack2(p.oox, p.oox));
+    const f32x2 ty = fma2(pack2(n0.z, n0.w), pack2(p.iy, p.iy), pack2(p.ooy, p.ooy));
+    const f32x2 tz = fma2(pack2(n1.x, n1.y), pack2(p.iz, p.iz), pack2(p.ooz, p.ooz));
+    const f32x2 hx = pack2(n1.z, n1.w), hy = pack2(n2.x, n2.y), hz = pack2(n2.z, n2.w);
+    float lxl, lxr, lyl, lyr, lzl, lzr, hxl, hxr, hyl, hyr, hzl, hzr;
+    unpack2(fma2(hx, pack2(-ax, -ax), tx), lxl, lxr);
+    unpack2(fma2(hy, pack2(-ay, -ay), ty), lyl, lyr);
+    unpack2(fma2(hz, pack2(-az, -az), tz), lzl, lzr);
+    unpack2(fma2(hx, pack2(ax, ax), tx), hxl, hxr);
+    unpack2(fma2(hy, pack2(ay, ay), ty), hyl, hyr);
+    unpack2(fma2(hz, pack2(az, az), tz), hzl, hzr);
+    tl = fmaxf(fmax3(lxl, lyl, lzl), t_min);
+    tr = fmaxf(fmax3(lxr, lyr, lzr), t_min);
+    hl = tl <= fminf(fmin3(hxl, hyl, hzl), t_max);
+    hr = tr <= fminf(fmin3(hxr, hyr, hzr), t_max);
 }
 
 // ---- primitive tests (bit-exact vs oracle sphere_roots / triangle_t) ---------------------------------------
@@ -433,8 +466,8 @@ __device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, cons
     }
     float tl, tr;
     if (COUNT) cnt.box += 2;
-    bool hl = box_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, p, t_min, t_max, tl);
-    bool hr = box_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, p, t_min, t_max, tr);
+    bool hl, hr;
+    box_hit2(n0, n1, n2, p, t_min, t_max, hl, hr, tl, tr);
     int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
     if (hl && hr) {
         bool left_first = tl <= tr;
