@@ -219,6 +219,25 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
     return r;
 }
 
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // Slab test of BOTH children of a node (already padded boxes as centre c and half extent h, interleaved L/R);
 // inclusive; entry distances in tl / tr.  Per axis  t_c = (c - o)/d,  [t_c - h|1/d|, t_c + h|1/d|]: three FFMA2
 // for the two boxes (no min/max to order the planes), then per box 2 FMNMX3 + 2 FMNMX + 1 FSETP.  A node visit
@@ -231,14 +250,18 @@ __device__ __forceinline__ void box_hit2(const float4 &n0, const float4 &n1, con
     const f32x2 tx = fma2(pack2(n0.x, n0.y), pack2(p.ix, p.ix), pack2(p.oox, p.oox));
     const f32x2 ty = fma2(pack2(n0.z, n0.w), pack2(p.iy, p.iy), pack2(p.ooy, p.ooy));
     const f32x2 tz = fma2(pack2(n1.x, n1.y), pack2(p.iz, p.iz), pack2(p.ooz, p.ooz));
-    const f32x2 hx = pack2(n1.z, n1.w), hy = pack2(n2.x, n2.y), hz = pack2(n2.z, n2.w);
+    // u = h * |1/d| then t_c -+ u: ptxas contracts each pair into one FFMA2 with the negation on the h pair and |.| on
+    // the broadcast scalar (operand modifiers, no extra registers)
+    const f32x2 ux = mul2(pack2(n1.z, n1.w), pack2(ax, ax));
+    const f32x2 uy = mul2(pack2(n2.x, n2.y), pack2(ay, ay));
+    const f32x2 uz = mul2(pack2(n2.z, n2.w), pack2(az, az));
     float lxl, lxr, lyl, lyr, lzl, lzr, hxl, hxr, hyl, hyr, hzl, hzr;
-    unpack2(fma2(hx, pack2(-ax, -ax), tx), lxl, lxr);
-    unpack2(fma2(hy, pack2(-ay, -ay), ty), lyl, lyr);
-    unpack2(fma2(hz, pack2(-az, -az), tz), lzl, lzr);
-    unpack2(fma2(hx, pack2(ax, ax), tx), hxl, hxr);
-    unpack2(fma2(hy, pack2(ay, ay), ty), hyl, hyr);
-    unpack2(fma2(hz, pack2(az, az), tz), hzl, hzr);
+    unpack2(sub2(tx, ux), lxl, lxr);
+    unpack2(sub2(ty, uy), lyl, lyr);
+    unpack2(sub2(tz, uz), lzl, lzr);
+    unpack2(add2(tx, ux), hxl, hxr);
+    unpack2(add2(ty, uy), hyl, hyr);
+    unpack2(add2(tz, uz), hzl, hzr);
     tl = fmaxf(fmax3(lxl, lyl, lzl), t_min);
     tr = fmaxf(fmax3(lxr, lyr, lzr), t_min);
     hl = tl <= fminf(fmin3(hxl, hyl, hzl), t_max);
