@@ -400,20 +400,21 @@ __device__ __forceinline__ void leaf_test(const float4 *__restrict__ leaves, con
         else if (type == PRIM_MSPHERE) ++cnt.msph;
         else ++cnt.tri;
     }
-    float4 a = __ldg(leaves + 3 * slot);
+    const float4 *rec = leaves + (size_t)(unsigned)slot * 3u; // one IMAD.WIDE (slot * 48 + base)
+    float4 a = __ldg(rec);
     float t;
     bool h;
     if (type == PRIM_SPHERE) {
         h = sphere_test(r, p, a.x, a.y, a.z, a.w, t_min, best.t, t);
     }
     else if (type == PRIM_MSPHERE) {
-        float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+        float4 b = __ldg(rec + 1), c = __ldg(rec + 2);
         float cx, cy, cz;
         msphere_center(a, b, c, r.tm, cx, cy, cz);
         h = sphere_test(r, p, cx, cy, cz, a.w, t_min, best.t, t);
     }
     else {
-        float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+        float4 b = __ldg(rec + 1), c = __ldg(rec + 2);
         double v0x = a.x, v0y = a.y, v0z = a.z;
         if (MTRI && type == PRIM_MTRIANGLE) { // the instance translates: meet the triangle where it is at the ray's time
             double tm = r.tm;
@@ -484,8 +485,11 @@ __device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, cons
         n0 = q[0]; n1 = q[1]; n2 = q[2]; n3 = q[3];
     }
     else {
-        ldg256(nodes + 4 * cur, n0, n1); // sm_100a 256-bit loads: a 64-byte node is two LDG.E.256, not four LDG.E.128
-        ldg256(nodes + 4 * cur + 2, n2, n3);
+        // sm_100a 256-bit loads: a 64-byte node is two LDG.E.256, not four LDG.E.128; the index is widened before
+        // it is scaled so that the address is ONE IMAD.WIDE (cur * 64 + base) instead of a shift and a multiply
+        const float4 *q = nodes + (size_t)(unsigned)cur * 4u;
+        ldg256(q, n0, n1);
+        ldg256(q + 2, n2, n3);
     }
     float tl, tr;
     if (COUNT) cnt.box += 2;

@@ -174,20 +174,21 @@ __device__ __forceinline__ void leaf_test_d(const float4 *__restrict__ leaves, c
         else if (type == PRIM_MSPHERE) ++cnt.msph;
         else ++cnt.tri;
     }
-    float4 a = __ldg(leaves + 3 * slot);
+    const float4 *rec = leaves + (size_t)(unsigned)slot * 3u; // one IMAD.WIDE (slot * 48 + base)
+    float4 a = __ldg(rec);
     double t;
     bool h;
     if (type == PRIM_SPHERE) {
         h = sphere_test_d(r, (double)a.x, (double)a.y, (double)a.z, (double)a.w, t_min, best.t, t);
     }
     else if (type == PRIM_MSPHERE) {
-        float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+        float4 b = __ldg(rec + 1), c = __ldg(rec + 2);
         double cx, cy, cz;
         msphere_center_d(a, b, c, r.tm, cx, cy, cz);
         h = sphere_test_d(r, cx, cy, cz, (double)a.w, t_min, best.t, t);
     }
     else {
-        float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+        float4 b = __ldg(rec + 1), c = __ldg(rec + 2);
         double v0x = a.x, v0y = a.y, v0z = a.z;
         if (type == PRIM_MTRIANGLE) {
             v0x = __fma_rn((double)a.w, r.tm, v0x);
