@@ -135,3 +135,97 @@ def test_cli_exit_codes(tmp_path, built_lib):
             assert r.returncode in (1, 99)
             r = subprocess.run([EXE, "-input", p, "-w", "32", "-h", "16", "-s", "1"], capture_output=True, text=True)
             assert r.returncode == 99 and "no CPU fallback" in r.stderr and "sphere count:    4" in r.stderr
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parser fuzz against the LIVE reference parser (oracle/_ref/libref_f.so = scene.h compiled as is)
+# ---------------------------------------------------------------------------------------------------------------
+def _num(rng, lo, hi):
+    """One number in one of the spellings std::stod accepts."""
+    v = rng.uniform(lo, hi)
+    style = rng.integers(0, 6)
+    if style == 0:
+        return "%d" % round(v)
+    if style == 1:
+        return "%.3f" % v
+    if style == 2:
+        return "%.6e" % v
+    if style == 3:
+        return ("+" if v >= 0 else "") + "%.2f" % v
+    if style == 4:
+        return repr(float(np.float32(v)))
+    return "%.10f" % v
+
+
+def _random_scene_text(seed):
+    rng = np.random.default_rng(seed)
+    sep = lambda: " " * int(rng.integers(1, 4)) if rng.uniform() < 0.8 else "\t"
+    L = []
+    join = lambda *w: sep().join(str(x) for x in w) + (" " * int(rng.integers(0, 3)))
+    L.append("# fuzz scene %d" % seed)
+    times = [_num(rng, 0, 0.4), _num(rng, 0.5, 1.5)] if rng.uniform() < 0.5 else []
+    L.append(join("camera", *[_num(rng, -6, 6) for _ in range(3)], *[_num(rng, -1, 1) for _ in range(3)], 0, 1, 0, _num(rng, 15, 60),
+                  _num(rng, 0, 0.3), _num(rng, 2, 9), *times))
+    names = []
+    for k in range(int(rng.integers(1, 7))):
+        n = "m%d" % k
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            L.append(join("material", n, "lambertian", *[_num(rng, 0, 1) for _ in range(3)]))
+        elif kind == 1:
+            L.append(join("material", n, "metal", *[_num(rng, 0, 1) for _ in range(3)], _num(rng, 0, 1.5)))
+        else:
+            L.append(join("material", n, "dielectric", _num(rng, 1.1, 2.4)))
+        names.append(n)
+        if rng.uniform() < 0.3:
+            L.append("")
+        if rng.uniform() < 0.2:
+            L.append("   sphere 0 0 0 1 %s" % n)  # leading blank: the line is ignored (prefix must sit at column 0)
+    pick = lambda: names[int(rng.integers(0, len(names)))]
+    n_obj = int(rng.integers(0, 3))
+    for o in range(n_obj):
+        nv, nt = int(rng.integers(3, 7)), int(rng.integers(1, 6))
+        L.append(join("obj_beg", nv, nt))
+        for _ in range(nv):
+            L.append(join("obj_vtx", *[_num(rng, -1, 1) for _ in range(3)]))
+        for _ in range(nt):
+            L.append(join("obj_tri", *[int(x) for x in rng.choice(nv, 3, replace=False)]))
+        L.append("obj_end")
+    for _ in range(int(rng.integers(1, 9))):
+        L.append(join("sphere", *[_num(rng, -5, 5) for _ in range(3)], _num(rng, 0.1, 2), pick()))
+    for _ in range(int(rng.integers(0, 4))):
+        L.append(join("msphere", *[_num(rng, -5, 5) for _ in range(6)], _num(rng, 0, 0.5), _num(rng, 0.6, 2), _num(rng, 0.1, 1), pick()))
+    for _ in range(int(rng.integers(0, 5)) if n_obj else 0):
+        xf = []
+        for _ in range(int(rng.integers(0, 4))):
+            op = "tsr"[int(rng.integers(0, 3))]
+            if op == "r":
+                xf += ["r", _num(rng, -180, 180), *[_num(rng, -1, 1) for _ in range(3)]]
+            elif op == "s":
+                xf += ["s", *[_num(rng, 0.2, 3) for _ in range(3)]]
+            else:
+                xf += ["t", *[_num(rng, -4, 4) for _ in range(3)]]
+        L.append(join("obj", int(rng.integers(0, n_obj)), pick(), *xf))
+    L.append("# end")
+    return "\n".join(L) + "\n"
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_parser_fuzz_vs_live_reference_parser(seed, tmp_path, built_lib):
+    """Random valid scene files (every number spelling std::stod takes, ragged whitespace, comments, ignored lines,
+    obj blocks with translate / scale / rotate chains): camera, materials and every primitive bit-identical to what
+    the reference's own parser (scene.h, compiled unmodified) builds."""
+    from oracle_lib import RefScene, have_ref
+    from rrt_b200 import Scene
+
+    if not have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    W, H = [(640, 360), (1200, 800), (333, 217)][seed % 3]
+    path = _write(tmp_path, _random_scene_text(1000 + seed))
+    ref = RefScene(path, W, H, "f")
+    want = ref.arrays()
+    got = Scene.from_file(path, W, H)
+    for k in ("camera", "materials", "spheres", "mspheres", "triangles"):
+        assert getattr(got.arrays, k).tobytes() == getattr(want, k).tobytes(), (seed, k)
+    c = got.counts()
+    assert [c[k] for k in ("materials", "spheres", "mspheres", "triangles", "objs", "obj_insts")] == [ref.counts[k] for k in ("materials", "spheres", "mspheres", "triangles", "objs", "obj_insts")]
