@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RRTB_ABI_VERSION 1
+#define RRTB_ABI_VERSION 2
 
 typedef enum rrtb_status {
     RRTB_OK = 0,
@@ -217,6 +217,14 @@ int rrtb_camera_rays_f64(rrtb_ctx *ctx, const rrtb_render_params *p, const int32
 int rrtb_bvh_size(rrtb_ctx *ctx, int32_t *n_prims);
 int rrtb_bvh_download(rrtb_ctx *ctx, uint32_t *morton, uint32_t *perm, int32_t *left, int32_t *right,
                       int32_t *parent, float *node_box, float *prim_box);
+/* The traversal tree the render kernels walk: the 4-wide collapse of the canonical LBVH above (greedy by surface
+ * area); *width = 4.  32 floats per node: c.x[4] c.y[4] c.z[4] h.x[4] h.y[4] h.z[4] (padded child boxes as centre /
+ * half extent), 4 child refs as int bits, 4 unused.  Child ref >= 0: node index; < 0: ~((sorted position << 2) |
+ * primitive type); an unused child slot has h = -inf.  Node 0 is the root; a parent always precedes its children.
+ * Test hook: the tree is derived data (closest hit does not depend on it); it is checked for being a partition of
+ * the primitives whose boxes enclose them (tests/test_gpu_edge_cases.py). */
+int rrtb_wide_size(rrtb_ctx *ctx, int32_t *n_nodes, int32_t *width);
+int rrtb_wide_download(rrtb_ctx *ctx, float *nodes, int32_t max_nodes);
 /* Philox4x32-10 known-answer hook: out[4*i..] = philox(ctr[4*i..], key) computed on the device. */
 int rrtb_philox(rrtb_ctx *ctx, const uint32_t *ctr4, int n, uint32_t key0, uint32_t key1, uint32_t *out4);
 /* material::scatter (material.h:21-32,50-57,76-96) on the device for explicit inputs.

@@ -16,7 +16,7 @@ SYMBOLS = [
     "rrtb_abi_version", "rrtb_create", "rrtb_destroy", "rrtb_last_error", "rrtb_device_info",
     "rrtb_scene_set", "rrtb_scene_stage_moving_triangles", "rrtb_camera_set", "rrtb_render", "rrtb_render_f64", "rrtb_render_device", "rrtb_resolve_device",
     "rrtb_accumulate_device", "rrtb_trace_closest", "rrtb_trace_closest_f64", "rrtb_camera_rays", "rrtb_camera_rays_f64",
-    "rrtb_bvh_size", "rrtb_bvh_download", "rrtb_philox", "rrtb_scatter", "rrtb_scatter_f64", "rrtb_probe_issue_rate", "rrtb_scene_parse_file", "rrtb_scene_free", "rrtb_scene_counts",
+    "rrtb_bvh_size", "rrtb_bvh_download", "rrtb_wide_size", "rrtb_wide_download", "rrtb_philox", "rrtb_scatter", "rrtb_scatter_f64", "rrtb_probe_issue_rate", "rrtb_scene_parse_file", "rrtb_scene_free", "rrtb_scene_counts",
     "rrtb_scene_camera", "rrtb_scene_materials", "rrtb_scene_spheres", "rrtb_scene_mspheres",
     "rrtb_scene_triangles", "rrtb_scene_mtriangle_count", "rrtb_scene_mtriangles", "rrtb_scene_upload", "rrtb_camera_derive", "rrtb_tonemap_rgb8", "rrtb_tonemap_rgb8_f64", "rrtb_write_png",
 ]
@@ -67,6 +67,8 @@ def load():
         "rrtb_scatter_f64": (C.c_int, [vp, vp, vp, C.c_int, vp]),
         "rrtb_bvh_size": (C.c_int, [vp, P(i32)]),
         "rrtb_bvh_download": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
+        "rrtb_wide_size": (C.c_int, [vp, P(i32), P(i32)]),
+        "rrtb_wide_download": (C.c_int, [vp, vp, i32]),
         "rrtb_philox": (C.c_int, [vp, vp, C.c_int, u32, u32, vp]),
         "rrtb_scatter": (C.c_int, [vp, vp, vp, C.c_int, vp]),
         "rrtb_probe_issue_rate": (C.c_int, [vp, P(C.c_double), P(C.c_double)]),
@@ -89,7 +91,7 @@ def load():
     for name in SYMBOLS:
         fn = getattr(lib, name)  # raises AttributeError if the library does not export it
         fn.restype, fn.argtypes = sig[name]
-    if lib.rrtb_abi_version() != 1:
+    if lib.rrtb_abi_version() != 2:
         raise ImportError("rrt_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -262,6 +262,16 @@ class Context:
         self._check(self.lib.rrtb_bvh_download(self.h, _vp(morton), _vp(perm), _vp(left), _vp(right), _vp(parent), _vp(node_box), _vp(prim_box)))
         return dict(morton=morton, perm=perm, left=left, right=right, parent=parent, node_box=node_box, prim_box=prim_box)
 
+    def wide_arrays(self):
+        """The W-wide traversal tree: dict(c=[m,3,W] centres, h=[m,3,W] half extents, ref=[m,W] child refs)."""
+        n, w = C.c_int32(), C.c_int32()
+        self._check(self.lib.rrtb_wide_size(self.h, C.byref(n), C.byref(w)))
+        n, w = n.value, w.value
+        raw = np.zeros((n, 8 * w), np.float32)
+        self._check(self.lib.rrtb_wide_download(self.h, _vp(raw), n))
+        return dict(c=raw[:, 0:3 * w].reshape(-1, 3, w).copy(), h=raw[:, 3 * w:6 * w].reshape(-1, 3, w).copy(),
+                    ref=raw[:, 6 * w:7 * w].copy().view(np.int32))
+
     def philox(self, ctr4, key0, key1):
         ctr4 = np.ascontiguousarray(ctr4, dtype=np.uint32).reshape(-1, 4)
         out = np.zeros_like(ctr4)

@@ -37,11 +37,21 @@ static int invalid(rrtb_ctx *ctx, const char *msg)
     return RRTB_ERR_INVALID;
 }
 
+// grow-only device buffer: reallocated only when the request exceeds what the member already holds
 template <typename T>
-static int dev_alloc(rrtb_ctx *ctx, T *&p, size_t count)
+static int dev_reserve(rrtb_ctx *ctx, T *&p, size_t count)
 {
     if (count == 0) count = 1;
-    RRTB_CUDA(ctx, cudaMalloc((void **)&p, count * sizeof(T)));
+    const size_t bytes = count * sizeof(T);
+    size_t &cap = ctx->capacity[(const void *)&p];
+    if (p && cap >= bytes) return RRTB_OK;
+    if (p) {
+        cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    RRTB_CUDA(ctx, cudaMalloc((void **)&p, bytes));
+    cap = bytes;
     return RRTB_OK;
 }
 
@@ -168,17 +178,23 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     if ((n_spheres && !spheres) || (n_mspheres && !mspheres) || (n_triangles && !triangles))
         return invalid(ctx, "null primitive array");
     const int n = (int)n_ll;
+    // everything is validated BEFORE the loaded scene is touched: a rejected call leaves it renderable
+    for (int i = 0; i < n_materials; ++i)
+        if (materials[i].type < 0 || materials[i].type > 2) return invalid(ctx, "unknown material type");
     for (int i = 0; i < n_spheres; ++i)
         if (spheres[i].material < 0 || spheres[i].material >= n_materials) return invalid(ctx, "sphere material index out of range");
-    for (int i = 0; i < n_mspheres; ++i)
+    for (int i = 0; i < n_mspheres; ++i) {
         if (mspheres[i].material < 0 || mspheres[i].material >= n_materials) return invalid(ctx, "msphere material index out of range");
+        // moving_sphere.h:27-30 divides by (time1 - time0)
+        if (!(mspheres[i].time1 != mspheres[i].time0)) return invalid(ctx, "moving sphere needs time0 != time1");
+    }
     for (int i = 0; i < n_triangles; ++i)
         if (triangles[i].material < 0 || triangles[i].material >= n_materials) return invalid(ctx, "triangle material index out of range");
     for (int i = 0; i < n_mtriangles; ++i)
         if (mtri[i].material < 0 || mtri[i].material >= n_materials) return invalid(ctx, "moving triangle material index out of range");
 
     RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
-    free_scene(ctx);
+    ctx->has_scene = false; // until the build below has succeeded
     ctx->cam = *cam;
     ctx->n_materials = n_materials;
     ctx->n_spheres = n_spheres;
@@ -191,87 +207,63 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     int rc;
     const int nb = (n + 255) / 256;
     const int n_seg = (n + 1023) / 1024;
-    if ((rc = dev_alloc(ctx, ctx->d_prim, (size_t)3 * n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_prim_info, (size_t)n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_materials, (size_t)n_materials))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_material_type, (size_t)n_materials))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_prim_box, (size_t)6 * n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_morton, (size_t)n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_keys, (size_t)n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_keys_tmp, (size_t)n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_left, (size_t)n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_right, (size_t)n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_parent, (size_t)2 * n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_node_box, (size_t)6 * n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_visit, (size_t)n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_nodes, (size_t)4 * n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_top_nodes, (size_t)4 * RRTB_TOP_NODES))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_n_top, (size_t)1))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_leaves, (size_t)3 * n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_leaf_info, (size_t)n))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_reduce, (size_t)nb * 7 + 16))) return rc;
-    if ((rc = dev_alloc(ctx, ctx->d_hist, (size_t)256 * n_seg + (size_t)(256 * n_seg + 4095) / 4096 + 1))) return rc; // + chunk sums
+    const size_t b_sph = (sizeof(rrtb_sphere) * (size_t)n_spheres + 15) & ~(size_t)15;
+    const size_t b_msph = (sizeof(rrtb_msphere) * (size_t)n_mspheres + 15) & ~(size_t)15;
+    const size_t b_tri = (sizeof(rrtb_triangle) * (size_t)n_triangles + 15) & ~(size_t)15;
+    const size_t b_mtri = (sizeof(rrtb_mtriangle) * (size_t)n_mtriangles + 15) & ~(size_t)15;
+    if ((rc = dev_reserve(ctx, ctx->d_prim, (size_t)3 * n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_prim_info, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_materials, (size_t)n_materials))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_material_type, (size_t)n_materials))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_prim_box, (size_t)6 * n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_morton, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_keys, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_keys_tmp, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_left, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_right, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_parent, (size_t)2 * n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_node_box, (size_t)6 * n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_visit, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_wnodes, (size_t)RRTB_NODE_F4 * n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_wq, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_collapse, (size_t)4))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_leaves, (size_t)3 * n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_leaf_info, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_reduce, (size_t)nb * 7 + 16))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_hist, (size_t)256 * n_seg + (size_t)(256 * n_seg + 4095) / 4096 + 1))) return rc; // + chunk sums
+    if ((rc = dev_reserve(ctx, ctx->d_stage, b_sph + b_msph + b_tri + b_mtri))) return rc;
 
     // materials -> (albedo.xyz, param) + type
     std::vector<float4> mats((size_t)n_materials);
     std::vector<int> mtypes((size_t)n_materials);
     for (int i = 0; i < n_materials; ++i) {
         const rrtb_material &m = materials[i];
-        if (m.type < 0 || m.type > 2) return invalid(ctx, "unknown material type");
         mats[i] = make_float4(m.albedo[0], m.albedo[1], m.albedo[2], m.param);
         mtypes[i] = m.type;
     }
 
-    // staged raw structs (freed after the build)
-    rrtb_sphere *d_sph = nullptr;
-    rrtb_msphere *d_msph = nullptr;
-    rrtb_triangle *d_tri = nullptr;
-    rrtb_mtriangle *d_mtri = nullptr;
-    auto cleanup = [&]() {
-        if (d_sph) cudaFree(d_sph);
-        if (d_msph) cudaFree(d_msph);
-        if (d_tri) cudaFree(d_tri);
-        if (d_mtri) cudaFree(d_mtri);
-    };
+    // raw structs, staged in one device buffer for k_prepare
+    rrtb_sphere *d_sph = (rrtb_sphere *)ctx->d_stage;
+    rrtb_msphere *d_msph = (rrtb_msphere *)(ctx->d_stage + b_sph);
+    rrtb_triangle *d_tri = (rrtb_triangle *)(ctx->d_stage + b_sph + b_msph);
+    rrtb_mtriangle *d_mtri = (rrtb_mtriangle *)(ctx->d_stage + b_sph + b_msph + b_tri);
     cudaStream_t st = ctx->stream;
-#define SET_CUDA(expr)                                                      \
-    do {                                                                    \
-        cudaError_t _e = (expr);                                            \
-        if (_e != cudaSuccess) {                                            \
-            cleanup();                                                      \
-            return cuda_fail(ctx, _e, #expr, __FILE__, __LINE__);           \
-        }                                                                   \
-    } while (0)
-    SET_CUDA(cudaEventRecord(ctx->ev0, st));
-    SET_CUDA(cudaMemcpyAsync(ctx->d_materials, mats.data(), sizeof(float4) * n_materials, cudaMemcpyHostToDevice, st));
-    SET_CUDA(cudaMemcpyAsync(ctx->d_material_type, mtypes.data(), sizeof(int) * n_materials, cudaMemcpyHostToDevice, st));
-    if (n_spheres) {
-        SET_CUDA(cudaMalloc((void **)&d_sph, sizeof(rrtb_sphere) * (size_t)n_spheres));
-        SET_CUDA(cudaMemcpyAsync(d_sph, spheres, sizeof(rrtb_sphere) * (size_t)n_spheres, cudaMemcpyHostToDevice, st));
-    }
-    if (n_mspheres) {
-        SET_CUDA(cudaMalloc((void **)&d_msph, sizeof(rrtb_msphere) * (size_t)n_mspheres));
-        SET_CUDA(cudaMemcpyAsync(d_msph, mspheres, sizeof(rrtb_msphere) * (size_t)n_mspheres, cudaMemcpyHostToDevice, st));
-    }
-    if (n_triangles) {
-        SET_CUDA(cudaMalloc((void **)&d_tri, sizeof(rrtb_triangle) * (size_t)n_triangles));
-        SET_CUDA(cudaMemcpyAsync(d_tri, triangles, sizeof(rrtb_triangle) * (size_t)n_triangles, cudaMemcpyHostToDevice, st));
-    }
-    if (n_mtriangles) {
-        SET_CUDA(cudaMalloc((void **)&d_mtri, sizeof(rrtb_mtriangle) * (size_t)n_mtriangles));
-        SET_CUDA(cudaMemcpyAsync(d_mtri, mtri.data(), sizeof(rrtb_mtriangle) * (size_t)n_mtriangles, cudaMemcpyHostToDevice, st));
-    }
-    rc = prepare_and_build(ctx, d_sph, d_msph, d_tri, d_mtri);
-    if (rc) {
-        cleanup();
-        return rc;
-    }
-    SET_CUDA(cudaEventRecord(ctx->ev1, st));
-    SET_CUDA(cudaStreamSynchronize(st));
+    RRTB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    RRTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_materials, mats.data(), sizeof(float4) * n_materials, cudaMemcpyHostToDevice, st));
+    RRTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_material_type, mtypes.data(), sizeof(int) * n_materials, cudaMemcpyHostToDevice, st));
+    if (n_spheres)
+        RRTB_CUDA(ctx, cudaMemcpyAsync(d_sph, spheres, sizeof(rrtb_sphere) * (size_t)n_spheres, cudaMemcpyHostToDevice, st));
+    if (n_mspheres)
+        RRTB_CUDA(ctx, cudaMemcpyAsync(d_msph, mspheres, sizeof(rrtb_msphere) * (size_t)n_mspheres, cudaMemcpyHostToDevice, st));
+    if (n_triangles)
+        RRTB_CUDA(ctx, cudaMemcpyAsync(d_tri, triangles, sizeof(rrtb_triangle) * (size_t)n_triangles, cudaMemcpyHostToDevice, st));
+    if (n_mtriangles)
+        RRTB_CUDA(ctx, cudaMemcpyAsync(d_mtri, mtri.data(), sizeof(rrtb_mtriangle) * (size_t)n_mtriangles, cudaMemcpyHostToDevice, st));
+    if ((rc = prepare_and_build(ctx, d_sph, d_msph, d_tri, d_mtri))) return rc;
+    RRTB_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    RRTB_CUDA(ctx, cudaStreamSynchronize(st)); // the host arrays (and mats / mtri above) may go away after this
     float ms = 0.f;
-    SET_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-#undef SET_CUDA
-    cleanup();
+    RRTB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->seconds_build = ms * 1e-3;
     ctx->has_scene = true;
     return RRTB_OK;
@@ -415,6 +407,7 @@ int rrtb_trace_closest(rrtb_ctx *ctx, const float *rays7, int n, float t_min, in
         ctx->err = "trace before rrtb_scene_set";
         return RRTB_ERR_NO_SCENE;
     }
+    if (!(t_min >= 0.0f)) return invalid(ctx, "t_min must be >= 0 (the reference uses 0.001, rrt.cu:49)");
     if (n == 0) return RRTB_OK;
     RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
     DevBuf dr, di, dt, drec;
@@ -482,6 +475,27 @@ int rrtb_bvh_download(rrtb_ctx *ctx, uint32_t *morton, uint32_t *perm, int32_t *
     return RRTB_OK;
 }
 
+int rrtb_wide_size(rrtb_ctx *ctx, int32_t *n_nodes, int32_t *width)
+{
+    if (!ctx || !n_nodes) return RRTB_ERR_INVALID;
+    if (width) *width = RRTB_WIDTH;
+    if (!ctx->has_scene) return RRTB_ERR_NO_SCENE;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    RRTB_CUDA(ctx, cudaMemcpy(n_nodes, ctx->d_collapse, sizeof(int), cudaMemcpyDeviceToHost)); // CollapseState::n_alloc
+    return RRTB_OK;
+}
+
+int rrtb_wide_download(rrtb_ctx *ctx, float *nodes, int32_t max_nodes)
+{
+    if (!ctx || !nodes || max_nodes < 0) return RRTB_ERR_INVALID;
+    int32_t n_nodes = 0;
+    int rc = rrtb_wide_size(ctx, &n_nodes, nullptr);
+    if (rc) return rc;
+    if (n_nodes > max_nodes) return invalid(ctx, "wide-node buffer too small");
+    RRTB_CUDA(ctx, cudaMemcpy(nodes, ctx->d_wnodes, sizeof(float4) * RRTB_NODE_F4 * (size_t)n_nodes, cudaMemcpyDeviceToHost));
+    return RRTB_OK;
+}
+
 int rrtb_philox(rrtb_ctx *ctx, const uint32_t *ctr4, int n, uint32_t key0, uint32_t key1, uint32_t *out4)
 {
     if (!ctx || !ctr4 || !out4 || n < 0) return RRTB_ERR_INVALID;
@@ -529,6 +543,7 @@ int rrtb_trace_closest_f64(rrtb_ctx *ctx, const double *rays7, int n, double t_m
         ctx->err = "trace before rrtb_scene_set";
         return RRTB_ERR_NO_SCENE;
     }
+    if (!(t_min >= 0.0)) return invalid(ctx, "t_min must be >= 0 (the reference uses 0.001, rrt.cu:49)");
     if (n == 0) return RRTB_OK;
     RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
     DevBuf dr, di, dt, drec;

@@ -12,7 +12,8 @@
 //   radix sort     4 stable LSD passes of 8 bits over the code (k_hist / k_scan / k_scatter)
 //   k_karras       Karras 2012 internal nodes from the sorted keys (delta = clz64 of key xor)
 //   k_refit        bottom-up boxes, second arrival at a node computes it (fminf/fmaxf: order independent)
-//   k_flatten_*    64-byte two-child nodes with padded boxes + leaf-ordered 48-byte primitive records
+//   k_collapse4    the 4-wide traversal tree: 128-byte nodes, padded child boxes as centre + half extent
+//   k_flatten_leaves  leaf-ordered 48-byte primitive records
 //
 // Every floating-point step that feeds the Morton code uses explicit _rn intrinsics so the codes, the
 // permutation and the topology are BIT-EXACT against oracle/rrt_oracle.c (tests/test_lbvh_parity.py).
@@ -455,51 +456,149 @@ __device__ __forceinline__ int prim_type(int id, int ns, int nms, int nt)
     return id < ns ? PRIM_SPHERE : (id < ns + nms ? PRIM_MSPHERE : (id < ns + nms + nt ? PRIM_TRIANGLE : PRIM_MTRIANGLE));
 }
 
-__global__ void __launch_bounds__(TPB) k_flatten_nodes(const uint64_t *__restrict__ keys, int n, int ns, int nms, int nt,
-                                                        const int *__restrict__ left, const int *__restrict__ right,
-                                                        const float *__restrict__ prim_box,
-                                                        const float *__restrict__ node_box,
-                                                        const BuildConsts *__restrict__ bc, float4 *__restrict__ nodes)
+// ---- 4-wide collapse of the canonical binary LBVH: the tree the render kernels traverse -----------------------------
+// A wide node takes a binary node b and opens, twice, its internal child of largest surface area, which leaves up to
+// four children (the greedy surface-area collapse of Wald et al. 2008 / Ylitie et al. 2017).  Wide nodes are created
+// top-down through a work list: wq[i] = the binary node that roots wide node i, written by the thread that processed
+// the parent (index taken from one atomic counter, so the array is in creation order: parents before children, roughly
+// breadth-first).  One persistent grid drains the list: a warp draws 32 consecutive indices and polls their entries;
+// an index whose entry never appears is past the end -- known once every primitive has been emitted as a leaf child
+// (leaves_done == n), after which no node can be created.  The producer of an entry always holds a LOWER index, which
+// was drawn earlier by a thread that is resident or finished, so the polling can not deadlock.
+struct CollapseState {
+    int n_alloc;     // wide nodes created so far (root included)
+    int ticket;      // next index to hand out
+    int leaves_done; // primitives emitted as leaf children
+};
+
+__global__ void __launch_bounds__(TPB) k_collapse_init(int *__restrict__ wq, int n, CollapseState *st)
 {
     const int i = blockIdx.x * TPB + threadIdx.x;
-    const int ni = n - 1;
-    const float pad = bc->pad;
-    if (n == 1) { // degenerate tree: both children of the root are the only leaf (as bvh.h:116-118 does)
-        if (i == 0) {
-            const float *b = prim_box;
-            float c[3], h[3];
-            for (int k = 0; k < 3; ++k) center_half(b[k], b[3 + k], pad, c[k], h[k]);
-            int enc = ~((0 << 2) | prim_type(0, ns, nms, nt));
-            nodes[0] = make_float4(c[0], c[0], c[1], c[1]);
-            nodes[1] = make_float4(c[2], c[2], h[0], h[0]);
-            nodes[2] = make_float4(h[1], h[1], h[2], h[2]);
-            nodes[3] = make_float4(__int_as_float(enc), __int_as_float(enc), 0.f, 0.f);
-        }
-        return;
+    if (i < n) wq[i] = i == 0 ? 0 : -1;
+    if (i == 0) {
+        st->n_alloc = 1;
+        st->ticket = 0;
+        st->leaves_done = 0;
     }
-    if (i >= ni) return;
-    int ref[2] = {left[i], right[i]};
-    float bx[2][6];
-    int enc[2];
-    for (int c = 0; c < 2; ++c) {
-        const float *b;
-        if (ref[c] >= 0) {
-            b = node_box + 6 * ref[c];
-            enc[c] = ref[c];
+}
+
+__device__ __forceinline__ float box_area6(const float *b)
+{
+    const float x = b[3] - b[0], y = b[4] - b[1], z = b[5] - b[2];
+    return x * y + y * z + z * x;
+}
+
+__device__ __forceinline__ void collapse_one(int i, int b, const uint64_t *__restrict__ keys, int n, int ns, int nms, int nt,
+                                             const int *__restrict__ left, const int *__restrict__ right,
+                                             const float *__restrict__ prim_box, const float *__restrict__ node_box,
+                                             float pad, int *wq, CollapseState *st, float4 *__restrict__ wnodes)
+{
+    constexpr int WD = RRTB_WIDTH;
+    int ch[WD];
+    int nc;
+    if (n == 1) { // degenerate tree: the only primitive is the root's only child
+        ch[0] = ~0;
+        nc = 1;
+    }
+    else {
+        ch[0] = left[b];
+        ch[1] = right[b];
+        nc = 2;
+        for (int rep = 0; rep < WD - 2; ++rep) {
+            int bi = -1;
+            float ba = -1.0f;
+            for (int c = 0; c < nc; ++c)
+                if (ch[c] >= 0) {
+                    const float ar = box_area6(node_box + 6 * ch[c]);
+                    if (ar > ba) {
+                        ba = ar;
+                        bi = c;
+                    }
+                }
+            if (bi < 0) break;
+            const int bb = ch[bi];
+            ch[bi] = left[bb];
+            ch[nc++] = right[bb];
+        }
+    }
+    float cx[WD], cy[WD], cz[WD], hx[WD], hy[WD], hz[WD];
+    int ref[WD];
+    int leaves = 0;
+    for (int c = 0; c < WD; ++c) {
+        if (c >= nc) { // unused slot: never hit
+            cx[c] = cy[c] = cz[c] = 0.f;
+            hx[c] = hy[c] = hz[c] = -__int_as_float(0x7f800000);
+            ref[c] = TRAV_DONE;
+            continue;
+        }
+        const float *bx;
+        if (ch[c] >= 0) {
+            const int j = atomicAdd(&st->n_alloc, 1);
+            *(volatile int *)(wq + j) = ch[c];
+            ref[c] = j;
+            bx = node_box + 6 * ch[c];
         }
         else {
-            int slot = ~ref[c];
-            int id = (int)(uint32_t)keys[slot];
-            b = prim_box + 6 * id;
-            enc[c] = ~((slot << 2) | prim_type(id, ns, nms, nt));
+            const int slot = ~ch[c];
+            const int id = (int)(uint32_t)keys[slot];
+            ref[c] = ~((slot << 2) | prim_type(id, ns, nms, nt));
+            bx = prim_box + 6 * id;
+            ++leaves;
         }
-        for (int k = 0; k < 3; ++k) center_half(b[k], b[3 + k], pad, bx[c][k], bx[c][3 + k]);
+        center_half(bx[0], bx[3], pad, cx[c], hx[c]);
+        center_half(bx[1], bx[4], pad, cy[c], hy[c]);
+        center_half(bx[2], bx[5], pad, cz[c], hz[c]);
     }
-    // children interleaved per component (rrtb_device.cuh "BVH node"): one FFMA2 serves both boxes
-    nodes[4 * i + 0] = make_float4(bx[0][0], bx[1][0], bx[0][1], bx[1][1]);
-    nodes[4 * i + 1] = make_float4(bx[0][2], bx[1][2], bx[0][3], bx[1][3]);
-    nodes[4 * i + 2] = make_float4(bx[0][4], bx[1][4], bx[0][5], bx[1][5]);
-    nodes[4 * i + 3] = make_float4(__int_as_float(enc[0]), __int_as_float(enc[1]), 0.f, 0.f);
+    float4 *w = wnodes + RRTB_NODE_F4 * (size_t)i;
+    w[0] = make_float4(cx[0], cx[1], cx[2], cx[3]);
+    w[1] = make_float4(cy[0], cy[1], cy[2], cy[3]);
+    w[2] = make_float4(cz[0], cz[1], cz[2], cz[3]);
+    w[3] = make_float4(hx[0], hx[1], hx[2], hx[3]);
+    w[4] = make_float4(hy[0], hy[1], hy[2], hy[3]);
+    w[5] = make_float4(hz[0], hz[1], hz[2], hz[3]);
+    w[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
+    w[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (leaves) {
+        __threadfence(); // the work-list entries written above are visible before the leaf count that ends the polling
+        atomicAdd(&st->leaves_done, leaves);
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_collapse4(const uint64_t *__restrict__ keys, int n, int ns, int nms, int nt,
+                                                    const int *__restrict__ left, const int *__restrict__ right,
+                                                    const float *__restrict__ prim_box, const float *__restrict__ node_box,
+                                                    const BuildConsts *__restrict__ bc, int *wq, CollapseState *st,
+                                                    float4 *__restrict__ wnodes)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const float pad = bc->pad;
+    const int max_nodes = max(n - 1, 1);
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&st->ticket, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= max_nodes) return;
+        const int i = base + (int)lane;
+        bool pending = i < max_nodes, past_end = false;
+        while (__any_sync(0xffffffffu, pending)) {
+            if (pending) {
+                int b = *(volatile int *)(wq + i);
+                if (b < 0 && *(volatile int *)&st->leaves_done == n) {
+                    __threadfence();
+                    b = *(volatile int *)(wq + i); // look again: the entry may have landed just before the last leaf
+                    if (b < 0) {
+                        pending = false;
+                        past_end = true;
+                    }
+                }
+                if (b >= 0) {
+                    collapse_one(i, b, keys, n, ns, nms, nt, left, right, prim_box, node_box, pad, wq, st, wnodes);
+                    pending = false;
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, past_end)) return; // every later index is past the end too
+    }
 }
 
 __global__ void __launch_bounds__(TPB) k_flatten_leaves(const uint64_t *__restrict__ keys, int n,
@@ -513,41 +612,6 @@ __global__ void __launch_bounds__(TPB) k_flatten_leaves(const uint64_t *__restri
     leaves[3 * k + 1] = prim[3 * id + 1];
     leaves[3 * k + 2] = prim[3 * id + 2];
     leaf_info[k] = info[id];
-}
-
-// The first RRTB_TOP_NODES nodes of the tree in breadth-first order, for staging in shared memory by the
-// render kernel (north_star: "top tree levels staged in shared memory").  Child refs that stay inside the
-// staged set are re-encoded as TOP_FLAG | position; everything else keeps its global encoding.  One thread:
-// the set is tiny (<= 112 nodes) and this runs once per scene.
-__global__ void k_build_top(const float4 *__restrict__ nodes, int n_internal, float4 *__restrict__ top, int *__restrict__ n_top_out)
-{
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    int queue[RRTB_TOP_NODES];
-    int count = 0;
-    if (n_internal > 0) queue[count++] = 0;
-    for (int i = 0; i < count; ++i) { // breadth-first: append internal children while there is room
-        const float4 n3 = nodes[4 * queue[i] + 3];
-        const int ch[2] = {__float_as_int(n3.x), __float_as_int(n3.y)};
-        for (int c = 0; c < 2; ++c)
-            if (ch[c] >= 0 && count < RRTB_TOP_NODES) queue[count++] = ch[c];
-    }
-    for (int i = 0; i < count; ++i) {
-        const int id = queue[i];
-        float4 n3 = nodes[4 * id + 3];
-        int ch[2] = {__float_as_int(n3.x), __float_as_int(n3.y)};
-        for (int c = 0; c < 2; ++c)
-            if (ch[c] >= 0)
-                for (int q = i + 1; q < count; ++q) // children are always later in breadth-first order
-                    if (queue[q] == ch[c]) {
-                        ch[c] = TOP_FLAG | q;
-                        break;
-                    }
-        top[4 * i + 0] = nodes[4 * id + 0];
-        top[4 * i + 1] = nodes[4 * id + 1];
-        top[4 * i + 2] = nodes[4 * id + 2];
-        top[4 * i + 3] = make_float4(__int_as_float(ch[0]), __int_as_float(ch[1]), 0.f, 0.f);
-    }
-    *n_top_out = count;
 }
 
 // exposed to rrtb_api.cu (scene upload): raw struct arrays are staged by the caller
@@ -599,25 +663,15 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
         int m1 = -1;
         RRTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_parent, &m1, sizeof(int), cudaMemcpyHostToDevice, st));
     }
-    const int nbn = (max(n - 1, 1) + TPB - 1) / TPB;
-    k_flatten_nodes<<<nbn, TPB, 0, st>>>(ctx->d_keys, n, ns, nms, nt, ctx->d_left, ctx->d_right, ctx->d_prim_box,
-                                         ctx->d_node_box, bc, ctx->d_nodes);
+    CollapseState *cs = (CollapseState *)ctx->d_collapse;
+    k_collapse_init<<<nb, TPB, 0, st>>>(ctx->d_wq, n, cs);
+    const int want_blocks = (max(n - 1, 1) + TPB - 1) / TPB;
+    k_collapse4<<<min(want_blocks, ctx->sm_count * 4), TPB, 0, st>>>(ctx->d_keys, n, ns, nms, nt, ctx->d_left, ctx->d_right,
+                                                                     ctx->d_prim_box, ctx->d_node_box, bc, ctx->d_wq, cs,
+                                                                     ctx->d_wnodes);
     k_flatten_leaves<<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_prim, ctx->d_prim_info, ctx->d_leaves,
                                          ctx->d_leaf_info);
     RRTB_CUDA(ctx, cudaGetLastError());
-    ctx->n_top = 0; // the breadth-first top copy is built on demand (build_top)
-    return RRTB_OK;
-}
-
-// The staged top of the tree is an option of the pool kernel (off by default, rrtb_render_pool.cuh), so its
-// single-thread builder (0.3 ms) runs only for a render that asks for it.
-int build_top(rrtb_ctx *ctx)
-{
-    if (ctx->n_top > 0) return RRTB_OK;
-    k_build_top<<<1, 32, 0, ctx->stream>>>(ctx->d_nodes, max(ctx->n_prims - 1, 1), ctx->d_top_nodes, ctx->d_n_top);
-    RRTB_CUDA(ctx, cudaGetLastError());
-    RRTB_CUDA(ctx, cudaMemcpyAsync(&ctx->n_top, ctx->d_n_top, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RRTB_OK;
 }
 
@@ -629,8 +683,9 @@ void free_scene(rrtb_ctx *ctx)
     };
     F(ctx->d_prim); F(ctx->d_prim_info); F(ctx->d_materials); F(ctx->d_material_type); F(ctx->d_prim_box);
     F(ctx->d_morton); F(ctx->d_keys); F(ctx->d_keys_tmp); F(ctx->d_left); F(ctx->d_right); F(ctx->d_parent);
-    F(ctx->d_node_box); F(ctx->d_visit); F(ctx->d_nodes); F(ctx->d_leaves); F(ctx->d_leaf_info); F(ctx->d_reduce);
-    F(ctx->d_hist); F(ctx->d_top_nodes); F(ctx->d_n_top);
+    F(ctx->d_node_box); F(ctx->d_visit); F(ctx->d_wnodes); F(ctx->d_wq); F(ctx->d_collapse); F(ctx->d_leaves);
+    F(ctx->d_leaf_info); F(ctx->d_reduce); F(ctx->d_hist); F(ctx->d_stage);
+    ctx->capacity.clear();
     ctx->has_scene = false;
 }
 

@@ -5,7 +5,7 @@
 // Replaces (file:line under /root/reference):
 //   curand XORWOW + wrappers        rrt.cu:81-89, rtweekend.h:80-91   -> Philox4x32-10, stateless
 //   camera::get_ray                 camera.h:31-38, rrt.cu:112-114
-//   aabb::hit                       aabb.h:18-93                      -> 6 FFMA + FMNMX, no divides
+//   aabb::hit                       aabb.h:18-93                      -> FFMA2 + FMNMX3 on 4 boxes, no divides
 //   sphere::hit / moving_sphere::hit sphere.h:33-58, moving_sphere.h:27-58
 //   triangle::hit                   triangle.h:35-75
 //   hit_record::set_face_normal     hittable.h:16-20
@@ -43,17 +43,18 @@ __device__ unsigned int g_rrtb_violations;
 //   moving tri.    a = (base.xyz, rate.x) b = (e1.xyz, rate.y) c = (e2.xyz, rate.z)   v0(time) = fma(rate, time, base)
 //                  (include/rrtb.h "rrtb_mtriangle"; the normal is recomputed at shading time)
 // leaf_info[k] = (object id, material index)
-// BVH node: 4 x float4 (64 B): padded boxes of both children + child refs, the two children INTERLEAVED per
-// component so that one packed FP32x2 instruction (sm_100a FFMA2) works on the left and the right box at once:
-//   n0 = (L.c.x, R.c.x, L.c.y, R.c.y)  n1 = (L.c.z, R.c.z, L.h.x, R.h.x)  n2 = (L.h.y, R.h.y, L.h.z, R.h.z)
-//   n3 = (bits(left ref), bits(right ref), -, -)                              c = centre, h = half extent
-// child ref >= 0: internal node index;  < 0: leaf, ~ref = (leaf slot << 2) | type
+// Traversal node: a 4-WIDE node collapsed from the canonical binary LBVH (rrtb_bvh.cu k_collapse4), 8 x float4
+// (128 B): the padded boxes of the four children as centre c and half extent h, one float4 per component, so that
+// one packed FP32x2 instruction (sm_100a FFMA2) works on two children at once and a node is 3 x LDG.E.256 + 1 x
+// LDG.E.128:
+//   w0 = c.x[0..3]  w1 = c.y[0..3]  w2 = c.z[0..3]  w3 = h.x[0..3]  w4 = h.y[0..3]  w5 = h.z[0..3]
+//   w6 = bits(child ref[0..3])      w7 = unused
+// child ref >= 0: wide node index;  < 0: leaf, ~ref = (leaf slot << 2) | type.  An unused child slot has
+// h = -inf (its slab test can never pass) and ref = TRAV_DONE.
 enum : int { PRIM_SPHERE = 0, PRIM_MSPHERE = 1, PRIM_TRIANGLE = 2, PRIM_MTRIANGLE = 3 };
 
 struct DeviceScene {
-    const float4 *nodes;     // [4 * max(n-1,1)]
-    const float4 *top_nodes; // [4 * n_top] breadth-first top of the tree, refs re-encoded with TOP_FLAG
-    int n_top;
+    const float4 *wnodes;    // [8 * n_wide] 4-wide traversal nodes, root = 0
     const float4 *leaves;    // [3 * n]   leaf order
     const int2 *leaf_info;   // [n]
     const float4 *flat_leaves; // [3 * n]  object-id order (scan mode)
@@ -238,34 +239,33 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
     return r;
 }
 
-// Slab test of BOTH children of a node (already padded boxes as centre c and half extent h, interleaved L/R);
-// inclusive; entry distances in tl / tr.  Per axis  t_c = (c - o)/d,  [t_c - h|1/d|, t_c + h|1/d|]: three FFMA2
-// for the two boxes (no min/max to order the planes), then per box 2 FMNMX3 + 2 FMNMX + 1 FSETP.  A node visit
-// costs 9 + 10 arithmetic instructions; the scalar form (FFMA + FMUL + 2 FADD per axis and box) cost 24 + 10,
-// and the min/max form before it 12 + 22 on the alu pipe that ncu showed as the busiest unit.
-__device__ __forceinline__ void box_hit2(const float4 &n0, const float4 &n1, const float4 &n2, const RayPre &p, float t_min,
-                                         float t_max, bool &hl, bool &hr, float &tl, float &tr)
+// Slab test of TWO children of a wide node at once (already padded boxes as centre c and half extent h; each
+// f32x2 holds the same component of the two children); inclusive; entry distances in ta / tb.  Per axis
+// t_c = (c - o)/d, [t_c - h|1/d|, t_c + h|1/d|]: three FFMA2 for the two boxes (no min/max to order the planes;
+// ptxas folds the negation and the |.| of the broadcast scalar into operand modifiers), then per box
+// 2 FMNMX3 + 2 FMNMX + 1 FSETP.  The scalar form cost 24 fma-pipe + 10 alu-pipe instructions per pair, the
+// min/max form before it 12 + 22 on the alu pipe that ncu showed as the busiest unit.
+__device__ __forceinline__ void box_hit_pair(f32x2 cx, f32x2 cy, f32x2 cz, f32x2 hx, f32x2 hy, f32x2 hz, const RayPre &p,
+                                             float t_min, float t_max, bool &ha, bool &hb, float &ta, float &tb)
 {
     const float ax = fabsf(p.ix), ay = fabsf(p.iy), az = fabsf(p.iz);
-    const f32x2 tx = fma2(pack2(n0.x, n0.y), pack2(p.ix, p.ix), pack2(p.oox, p.oox));
-    const f32x2 ty = fma2(pack2(n0.z, n0.w), pack2(p.iy, p.iy), pack2(p.ooy, p.ooy));
-    const f32x2 tz = fma2(pack2(n1.x, n1.y), pack2(p.iz, p.iz), pack2(p.ooz, p.ooz));
-    // u = h * |1/d| then t_c -+ u: ptxas contracts each pair into one FFMA2 with the negation on the h pair and |.| on
-    // the broadcast scalar (operand modifiers, no extra registers)
-    const f32x2 ux = mul2(pack2(n1.z, n1.w), pack2(ax, ax));
-    const f32x2 uy = mul2(pack2(n2.x, n2.y), pack2(ay, ay));
-    const f32x2 uz = mul2(pack2(n2.z, n2.w), pack2(az, az));
-    float lxl, lxr, lyl, lyr, lzl, lzr, hxl, hxr, hyl, hyr, hzl, hzr;
-    unpack2(sub2(tx, ux), lxl, lxr);
-    unpack2(sub2(ty, uy), lyl, lyr);
-    unpack2(sub2(tz, uz), lzl, lzr);
-    unpack2(add2(tx, ux), hxl, hxr);
-    unpack2(add2(ty, uy), hyl, hyr);
-    unpack2(add2(tz, uz), hzl, hzr);
-    tl = fmaxf(fmax3(lxl, lyl, lzl), t_min);
-    tr = fmaxf(fmax3(lxr, lyr, lzr), t_min);
-    hl = tl <= fminf(fmin3(hxl, hyl, hzl), t_max);
-    hr = tr <= fminf(fmin3(hxr, hyr, hzr), t_max);
+    const f32x2 tx = fma2(cx, pack2(p.ix, p.ix), pack2(p.oox, p.oox));
+    const f32x2 ty = fma2(cy, pack2(p.iy, p.iy), pack2(p.ooy, p.ooy));
+    const f32x2 tz = fma2(cz, pack2(p.iz, p.iz), pack2(p.ooz, p.ooz));
+    const f32x2 ux = mul2(hx, pack2(ax, ax));
+    const f32x2 uy = mul2(hy, pack2(ay, ay));
+    const f32x2 uz = mul2(hz, pack2(az, az));
+    float lxa, lxb, lya, lyb, lza, lzb, hxa, hxb, hya, hyb, hza, hzb;
+    unpack2(sub2(tx, ux), lxa, lxb);
+    unpack2(sub2(ty, uy), lya, lyb);
+    unpack2(sub2(tz, uz), lza, lzb);
+    unpack2(add2(tx, ux), hxa, hxb);
+    unpack2(add2(ty, uy), hya, hyb);
+    unpack2(add2(tz, uz), hza, hzb);
+    ta = fmaxf(fmax3(lxa, lya, lza), t_min);
+    tb = fmaxf(fmax3(lxb, lyb, lzb), t_min);
+    ha = ta <= fminf(fmin3(hxa, hya, hza), t_max);
+    hb = tb <= fminf(fmin3(hxb, hyb, hzb), t_max);
 }
 
 // ---- primitive tests (bit-exact vs oracle sphere_roots / triangle_t) ---------------------------------------
@@ -451,20 +451,27 @@ __device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, 
     return best;
 }
 
-// ---- closest hit: LBVH traversal (replaces bvh_node::hit recursion, bvh.h:167-175) -------------------------
+// ---- closest hit: traversal of the 4-wide tree (replaces bvh_node::hit recursion, bvh.h:167-175) -----------
 // Iterative and STEP-WISE so that a warp-level scheduler can interleave it with other work:
-//   cur >= 0          internal node to visit  -> node_step: one 64-byte node fetch tests both children,
-//                     near child first, far child pushed
+//   cur >= 0          wide node to visit      -> wide_step: one 128-byte node fetch tests four children; the
+//                     nearest hit child is next, the other hit children are pushed
 //   cur <  0          a leaf reference        -> leaf_step: exact primitive test, then pop
 //   cur == TRAV_DONE  traversal finished
-// Stack entries live in local memory (L1-resident); the depth of a 30-bit-Morton + index-tiebreak Karras
-// tree is <= 62.
-#define RRTB_STACK 64
+// Every child that is hit gets a KEY = the bits of its entry distance with the two low mantissa bits replaced by
+// its slot: non-negative floats order as integers, so the nearest child is one 4-input unsigned minimum (2 VIMNMX3),
+// its slot comes with it, and equal distances can not tie.  The other hit children are pushed in slot order.
+// Measured and dropped (profiles/README.md, round 2): pushing the keys with the references so that a leaf whose
+// entry distance already exceeds the closest hit is skipped at pop time (-12 % leaf tests, but twice the local-memory
+// traffic: 5 % slower), a full sort of the hit children (more instructions than the visits it saves), and the
+// binary tree itself (two children per node: 3 % slower on the headline scene, 10 % on the 1.1 M-primitive one).
+// A collapsed tree is never deeper than the binary tree it comes from (<= 62 levels for 30-bit Morton codes with
+// an index tie-break) and a visit pushes at most three entries, so 192 entries can not overflow; the entries
+// live in local memory (L1-resident).
+#define RRTB_WIDTH 4
+#define RRTB_NODE_F4 (2 * RRTB_WIDTH) // float4 per traversal node
+#define RRTB_STACK 192
 #define TRAV_DONE ((int)0x80000000)
-// internal-node refs with this bit set index the breadth-first "top" copy of the tree that the pool kernel
-// stages in shared memory (node counts are < 2^28, so bit 30 is free)
-#define TOP_FLAG 0x40000000
-#define RRTB_TOP_NODES 112
+#define KEY_MISS (-1) // as unsigned the largest key, as signed below every real key
 
 // 32-byte read-only load (PTX ISA 8.8 ld.global.nc.v8.f32, SASS LDG.E.256.CONSTANT; p must be 32-byte aligned)
 __device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b)
@@ -474,52 +481,59 @@ __device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b)
         : "l"(p));
 }
 
-// TOP = true: refs carrying TOP_FLAG are fetched from `top` (shared memory), the others from `nodes` (global)
-template <bool COUNT, bool TOP = false>
-__device__ __forceinline__ void node_step(const float4 *__restrict__ nodes, const RayPre &p, float t_min, float t_max,
-                                          int &cur, int &sp, int *stack, TravCounters &cnt, const float4 *top = nullptr)
+__device__ __forceinline__ void trav_pop(int &cur, int &sp, const int *stk)
 {
-    float4 n0, n1, n2, n3;
-    if (TOP && (cur & TOP_FLAG)) {
-        const float4 *q = top + 4 * (cur & ~TOP_FLAG);
-        n0 = q[0]; n1 = q[1]; n2 = q[2]; n3 = q[3];
+    cur = sp > 0 ? stk[--sp] : TRAV_DONE;
+}
+
+// t_min must be >= 0 (keys order as integers only for non-negative distances); rrtb_trace_closest checks it
+template <bool COUNT>
+__device__ __forceinline__ void wide_step(const float4 *__restrict__ wnodes, const RayPre &p, float t_min, float t_max,
+                                          int &cur, int &sp, int *stk, TravCounters &cnt)
+{
+    // the index is widened before it is scaled so that the address is ONE IMAD.WIDE (cur * 128 + base)
+    const float4 *q = wnodes + (size_t)(unsigned)cur * (unsigned)RRTB_NODE_F4;
+    if (COUNT) cnt.box += RRTB_WIDTH;
+    float4 cx, cy, cz, hx, hy, hz;
+    ldg256(q, cx, cy);
+    ldg256(q + 2, cz, hx);
+    ldg256(q + 4, hy, hz);
+    const int4 rf = __ldg(reinterpret_cast<const int4 *>(q + 6));
+    bool h0, h1, h2, h3;
+    float t0, t1, t2, t3;
+    box_hit_pair(pack2(cx.x, cx.y), pack2(cy.x, cy.y), pack2(cz.x, cz.y), pack2(hx.x, hx.y), pack2(hy.x, hy.y),
+                 pack2(hz.x, hz.y), p, t_min, t_max, h0, h1, t0, t1);
+    box_hit_pair(pack2(cx.z, cx.w), pack2(cy.z, cy.w), pack2(cz.z, cz.w), pack2(hx.z, hx.w), pack2(hy.z, hy.w),
+                 pack2(hz.z, hz.w), p, t_min, t_max, h2, h3, t2, t3);
+    const int k0 = h0 ? (__float_as_int(t0) & ~3) : KEY_MISS;
+    const int k1 = h1 ? ((__float_as_int(t1) & ~3) | 1) : KEY_MISS;
+    const int k2 = h2 ? ((__float_as_int(t2) & ~3) | 2) : KEY_MISS;
+    const int k3 = h3 ? ((__float_as_int(t3) & ~3) | 3) : KEY_MISS;
+    // unsigned minimum: a real key (non-negative float bits) beats KEY_MISS
+    const int m = (int)min(min((unsigned)k0, (unsigned)k1), min((unsigned)k2, (unsigned)k3));
+    if (m < 0) { // no child hit
+        trav_pop(cur, sp, stk);
+        return;
     }
-    else {
-        // sm_100a 256-bit loads: a 64-byte node is two LDG.E.256, not four LDG.E.128; the index is widened before
-        // it is scaled so that the address is ONE IMAD.WIDE (cur * 64 + base) instead of a shift and a multiply
-        const float4 *q = nodes + (size_t)(unsigned)cur * 4u;
-        ldg256(q, n0, n1);
-        ldg256(q + 2, n2, n3);
-    }
-    float tl, tr;
-    if (COUNT) cnt.box += 2;
-    bool hl, hr;
-    box_hit2(n0, n1, n2, p, t_min, t_max, hl, hr, tl, tr);
-    int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
-    if (hl && hr) {
-        bool left_first = tl <= tr;
-        RRTB_CHECK(sp >= 0 && sp < RRTB_STACK);
-        stack[sp++] = left_first ? cr : cl;
-        cur = left_first ? cl : cr;
-    }
-    else if (hl) {
-        cur = cl;
-    }
-    else if (hr) {
-        cur = cr;
-    }
-    else {
-        cur = sp > 0 ? stack[--sp] : TRAV_DONE;
-    }
+    // SIGNED k > m: false for the nearest (equal) and for a miss (-1)
+    RRTB_CHECK(sp >= 0 && sp + 3 <= RRTB_STACK);
+    if (k0 > m) stk[sp++] = rf.x;
+    if (k1 > m) stk[sp++] = rf.y;
+    if (k2 > m) stk[sp++] = rf.z;
+    if (k3 > m) stk[sp++] = rf.w;
+    cur = rf.w;
+    if (k2 == m) cur = rf.z;
+    if (k1 == m) cur = rf.y;
+    if (k0 == m) cur = rf.x;
 }
 
 template <bool COUNT, bool MTRI = true>
 __device__ __forceinline__ void leaf_step(const float4 *__restrict__ leaves, const int2 *__restrict__ info, const Ray &r,
-                                          const RayPre &p, float t_min, Hit &best, int &cur, int &sp, int *stack,
+                                          const RayPre &p, float t_min, Hit &best, int &cur, int &sp, const int *stk,
                                           TravCounters &cnt)
 {
     leaf_test<COUNT, MTRI>(leaves, info, (~cur) >> 2, (~cur) & 3, r, p, t_min, best, cnt);
-    cur = sp > 0 ? stack[--sp] : TRAV_DONE;
+    trav_pop(cur, sp, stk);
 }
 
 template <bool COUNT>
@@ -534,7 +548,7 @@ __device__ __forceinline__ Hit closest_bvh(const DeviceScene &s, const Ray &r, c
     int sp = 0;
     int cur = 0;
     while (cur != TRAV_DONE) {
-        if (cur >= 0) node_step<COUNT>(s.nodes, p, t_min, best.t, cur, sp, stack, cnt);
+        if (cur >= 0) wide_step<COUNT>(s.wnodes, p, t_min, best.t, cur, sp, stack, cnt);
         else leaf_step<COUNT>(s.leaves, s.leaf_info, r, p, t_min, best, cur, sp, stack, cnt);
     }
     return best;

@@ -221,7 +221,7 @@ __device__ __forceinline__ HitD closest_scan_d(const DeviceScene &s, const RayD 
     return best;
 }
 
-// bvh_node::hit (bvh.h:167-175): the float integrator's node_step on the float view of the ray; the running
+// bvh_node::hit (bvh.h:167-175): the float integrator's wide_step on the float view of the ray; the running
 // closest distance is rounded UP and t_min DOWN when they enter the slab test
 template <bool COUNT>
 __device__ __forceinline__ HitD closest_bvh_d(const DeviceScene &s, const RayD &r, double t_min, TravCounters &cnt)
@@ -236,11 +236,11 @@ __device__ __forceinline__ HitD closest_bvh_d(const DeviceScene &s, const RayD &
     int cur = 0;
     while (cur != TRAV_DONE) {
         if (cur >= 0) {
-            node_step<COUNT>(s.nodes, p, t_min_f, __double2float_ru(best.t), cur, sp, stack, cnt);
+            wide_step<COUNT>(s.wnodes, p, t_min_f, __double2float_ru(best.t), cur, sp, stack, cnt);
         }
         else {
             leaf_test_d<COUNT>(s.leaves, s.leaf_info, (~cur) >> 2, (~cur) & 3, r, t_min, best, cnt);
-            cur = sp > 0 ? stack[--sp] : TRAV_DONE;
+            trav_pop(cur, sp, stack);
         }
     }
     return best;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/rrtb.h"
@@ -39,10 +40,9 @@ struct rrtb_ctx {
     float *d_node_box = nullptr;    // [6(n-1)]
     int *d_visit = nullptr;         // [n-1]
     // device: traversal structures
-    float4 *d_nodes = nullptr;      // [4*max(n-1,1)]
-    float4 *d_top_nodes = nullptr;  // [4*RRTB_TOP_NODES] breadth-first copy of the top of the tree (smem staging)
-    int *d_n_top = nullptr;
-    int n_top = 0;
+    float4 *d_wnodes = nullptr;     // [8*max(n-1,1)] 4-wide traversal nodes (rrtb_bvh.cu k_collapse4)
+    int *d_wq = nullptr;            // [n] collapse work list: binary node that roots wide node i
+    int *d_collapse = nullptr;      // CollapseState (wide-node count, ticket, leaves emitted)
     float4 *d_leaves = nullptr;     // [3n] leaf order
     int2 *d_leaf_info = nullptr;    // [n]
     // scratch
@@ -53,6 +53,10 @@ struct rrtb_ctx {
     unsigned long long *d_accum = nullptr;    // host-path accumulator (3*W*H)
     float *d_rgb = nullptr;                   // host-path float framebuffer
     size_t accum_elems = 0;
+    unsigned char *d_stage = nullptr;         // raw scene structs of the last upload (input of k_prepare)
+    // Device buffers are grow-only: rrtb_scene_set re-uses them when the next scene fits (a frame loop that re-sends
+    // its scene pays no cudaMalloc / cudaFree).  Capacity in bytes, keyed by the address of the pointer member.
+    std::unordered_map<const void *, size_t> capacity;
 };
 
 namespace rrtb {
@@ -68,7 +72,6 @@ int cuda_fail(rrtb_ctx *ctx, cudaError_t e, const char *expr, const char *file, 
 
 // rrtb_bvh.cu
 void free_scene(rrtb_ctx *ctx);
-int build_top(rrtb_ctx *ctx); // breadth-first copy of the top of the tree, on demand (RRTB_STAGE_TOP)
 
 // rrtb_render.cu
 DeviceScene device_scene(const rrtb_ctx *ctx);

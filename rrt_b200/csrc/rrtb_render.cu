@@ -28,6 +28,10 @@ namespace rrtb {
 
 static constexpr int RENDER_TPB = 256;
 static constexpr int CHUNK = 16; // samples per work item
+#ifndef RRTB_NODE_UNROLL
+#define RRTB_NODE_UNROLL 2
+#endif
+static constexpr int NODE_UNROLL = RRTB_NODE_UNROLL; // wide-node visits between two continue-votes of the pool scheduler
 
 struct RenderArgs {
     DeviceScene scene;
@@ -321,9 +325,7 @@ int launch_probe(rrtb_ctx *ctx, int mix, double *lane_instr_per_s)
 DeviceScene device_scene(const rrtb_ctx *ctx)
 {
     DeviceScene s;
-    s.nodes = ctx->d_nodes;
-    s.top_nodes = ctx->d_top_nodes;
-    s.n_top = ctx->n_top;
+    s.wnodes = ctx->d_wnodes;
     s.leaves = ctx->d_leaves;
     s.leaf_info = ctx->d_leaf_info;
     s.flat_leaves = ctx->d_prim;
@@ -374,10 +376,10 @@ static int launch_persistent(rrtb_ctx *ctx, K kernel, const RenderArgs &args, in
 }
 
 template <class P, typename K>
-static int launch_pool(rrtb_ctx *ctx, K kernel, const RenderArgs &args, int *blocks_out, bool stage_top)
+static int launch_pool(rrtb_ctx *ctx, K kernel, const RenderArgs &args, int *blocks_out)
 {
     constexpr int POOL = P::POOL;
-    const int smem = (int)(sizeof(WarpPoolT<typename P::real, POOL>) * POOL_WARPS + (stage_top ? sizeof(float4) * 4 * RRTB_TOP_NODES : 0));
+    const int smem = (int)(sizeof(WarpPoolT<typename P::real, POOL>) * POOL_WARPS);
     RRTB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
     RRTB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RENDER_TPB, smem));
@@ -434,12 +436,20 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     a.th_shade = 32;
     a.th_leaf = 8;
     a.step_iters = 8;
-    if (const char *e = getenv("RRTB_STEP_ITERS")) a.step_iters = atoi(e);
     a.th_node = 12;
-    if (const char *e = getenv("RRTB_TH_NODE")) a.th_node = atoi(e);
-    if (const char *e = getenv("RRTB_TH_FETCH")) a.th_fetch = atoi(e); // tuning aids
-    if (const char *e = getenv("RRTB_TH_SHADE")) a.th_shade = atoi(e);
-    if (const char *e = getenv("RRTB_TH_LEAF")) a.th_leaf = atoi(e);
+#ifdef RRTB_TUNING // tuning build only (make tune): scheduler thresholds from the environment, clamped to what the kernel assumes
+    auto knob = [](const char *name, int dflt, int lo, int hi) {
+        const char *e = getenv(name);
+        if (!e) return dflt;
+        const int v = atoi(e);
+        return v < lo ? lo : (v > hi ? hi : v);
+    };
+    a.step_iters = knob("RRTB_STEP_ITERS", a.step_iters, 1, 1 << 20);
+    a.th_node = knob("RRTB_TH_NODE", a.th_node, 1, 32);
+    a.th_fetch = knob("RRTB_TH_FETCH", a.th_fetch, 1, 32);
+    a.th_shade = knob("RRTB_TH_SHADE", a.th_shade, 1, 32);
+    a.th_leaf = knob("RRTB_TH_LEAF", a.th_leaf, 1, 32);
+#endif
     a.queue = ctx->d_counters;
 
     RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -450,8 +460,8 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
         const bool bvh = ctx->use_bvh != 0, cnt = p->count_rays != 0;
         int rc;
         if (f64 && use_pool) { // the pool scheduler over the double path policy
-            if (cnt) rc = launch_pool<PathF64>(ctx, k_render_pool<true, 2, false, true, PathF64>, a, &blocks, false);
-            else rc = launch_pool<PathF64>(ctx, k_render_pool<false, 2, false, true, PathF64>, a, &blocks, false);
+            if (cnt) rc = launch_pool<PathF64>(ctx, k_render_pool<true, NODE_UNROLL, true, PathF64>, a, &blocks);
+            else rc = launch_pool<PathF64>(ctx, k_render_pool<false, NODE_UNROLL, true, PathF64>, a, &blocks);
         }
         else if (f64) {
             if (bvh && cnt) rc = launch_persistent(ctx, k_render_f64<true, true>, a, &blocks);
@@ -460,16 +470,12 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
             else rc = launch_persistent(ctx, k_render_f64<false, false>, a, &blocks);
         }
         else if (use_pool) {
-            bool stage_top = false; // option, see rrtb_render_pool.cuh
-            if (const char *e = getenv("RRTB_STAGE_TOP")) stage_top = atoi(e) != 0;
-            if (stage_top && (rc = build_top(ctx))) return rc;
             if (ctx->n_mtriangles > 0) { // scenes with moving triangles get the variant that knows them
-                if (cnt) rc = launch_pool<PathF32>(ctx, k_render_pool<true, 2, false, true>, a, &blocks, false);
-                else rc = launch_pool<PathF32>(ctx, k_render_pool<false, 2, false, true>, a, &blocks, false);
+                if (cnt) rc = launch_pool<PathF32>(ctx, k_render_pool<true, NODE_UNROLL, true>, a, &blocks);
+                else rc = launch_pool<PathF32>(ctx, k_render_pool<false, NODE_UNROLL, true>, a, &blocks);
             }
-            else if (cnt) rc = launch_pool<PathF32>(ctx, k_render_pool<true, 2, false>, a, &blocks, false);
-            else if (stage_top) rc = launch_pool<PathF32>(ctx, k_render_pool<false, 2, true>, a, &blocks, true);
-            else rc = launch_pool<PathF32>(ctx, k_render_pool<false, 2, false>, a, &blocks, false);
+            else if (cnt) rc = launch_pool<PathF32>(ctx, k_render_pool<true, NODE_UNROLL, false>, a, &blocks);
+            else rc = launch_pool<PathF32>(ctx, k_render_pool<false, NODE_UNROLL, false>, a, &blocks);
         }
         else if (bvh && cnt) rc = launch_render_t<true, true>(ctx, a, &blocks);
         else if (bvh) rc = launch_render_t<true, false>(ctx, a, &blocks);

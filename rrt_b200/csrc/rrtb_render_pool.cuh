@@ -32,6 +32,10 @@
 #pragma once
 #include "rrtb_device_f64.cuh"
 
+#ifndef RRTB_POOL
+#define RRTB_POOL 96 // float integrator: path slots per warp (64 / 80 / 112 measured slower, profiles/README.md)
+#endif
+
 namespace rrtb {
 
 static constexpr int POOL_WARPS = RENDER_TPB / 32;
@@ -54,7 +58,7 @@ struct PathF32 { // the float integrator (rrtb_device.cuh)
     typedef Ray RayT;
     typedef Hit HitT;
     typedef HitRecord RecT;
-    static constexpr int POOL = 96;         // path slots per warp
+    static constexpr int POOL = RRTB_POOL;  // path slots per warp
     static constexpr int BLOCKS_PER_SM = 4; // 64 registers
     static __device__ __forceinline__ RayPre pre(const Ray &r) { return ray_pre(r); }
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
@@ -70,9 +74,9 @@ struct PathF32 { // the float integrator (rrtb_device.cuh)
     }
     template <bool COUNT, bool MTRI>
     static __device__ __forceinline__ void leaf(const float4 *__restrict__ leaves, const int2 *__restrict__ info, const Ray &r,
-                                                const RayPre &p, Hit &best, int &cur, int &sp, int *stack, TravCounters &tc)
+                                                const RayPre &p, Hit &best, int &cur, int &sp, const int *stk, TravCounters &tc)
     {
-        leaf_step<COUNT, MTRI>(leaves, info, r, p, 0.001f, best, cur, sp, stack, tc);
+        leaf_step<COUNT, MTRI>(leaves, info, r, p, 0.001f, best, cur, sp, stk, tc);
     }
     template <bool MTRI>
     static __device__ __forceinline__ HitRecord record(const float4 *__restrict__ leaves, const int2 *__restrict__ info,
@@ -124,10 +128,10 @@ struct PathF64 { // the double integrator (rrtb_device_f64.cuh); bit-exact again
     }
     template <bool COUNT, bool MTRI>
     static __device__ __forceinline__ void leaf(const float4 *__restrict__ leaves, const int2 *__restrict__ info, const RayD &r,
-                                                const RayPre &, HitD &best, int &cur, int &sp, int *stack, TravCounters &tc)
+                                                const RayPre &, HitD &best, int &cur, int &sp, const int *stk, TravCounters &tc)
     {
         leaf_test_d<COUNT>(leaves, info, (~cur) >> 2, (~cur) & 3, r, 0.001, best, tc);
-        cur = sp > 0 ? stack[--sp] : TRAV_DONE;
+        trav_pop(cur, sp, stk);
     }
     template <bool MTRI>
     static __device__ __forceinline__ HitRecordD record(const float4 *__restrict__ leaves, const int2 *__restrict__ info,
@@ -156,7 +160,7 @@ struct PathF64 { // the double integrator (rrtb_device_f64.cuh); bit-exact again
     }
 };
 
-template <bool COUNT_RAYS, int NODE_UNROLL, bool STAGE_TOP, bool MTRI = false, class P = PathF32>
+template <bool COUNT_RAYS, int NODE_UNROLL, bool MTRI = false, class P = PathF32>
 __global__ void __launch_bounds__(RENDER_TPB, P::BLOCKS_PER_SM) k_render_pool(const RenderArgs a)
 {
     typedef typename P::real real;
@@ -167,20 +171,9 @@ __global__ void __launch_bounds__(RENDER_TPB, P::BLOCKS_PER_SM) k_render_pool(co
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const DeviceScene &s = a.scene;
-    const float4 *__restrict__ nodes = s.nodes;
+    const float4 *__restrict__ wnodes = s.wnodes;
     const float4 *__restrict__ leaves = s.leaves;
     const int2 *__restrict__ info = s.leaf_info;
-
-    // STAGE_TOP (north_star: "top tree levels staged in shared memory"): the first <= RRTB_TOP_NODES nodes in
-    // breadth-first order sit behind the pools.  Measured on B200 (profiles/README.md) this LOSES 9 % on
-    // final.txt -- the hot top of the tree is L1-resident anyway, the 7 KB come out of L1 and every node
-    // visit pays a shared-or-global branch -- so it is compiled as an option and off by default.
-    float4 *top = reinterpret_cast<float4 *>(smem_raw + sizeof(WarpPool) * POOL_WARPS);
-    if (STAGE_TOP) {
-        for (int k = threadIdx.x; k < 4 * s.n_top; k += RENDER_TPB) top[k] = __ldg(s.top_nodes + k);
-        __syncthreads();
-    }
-    const int root = (STAGE_TOP && s.n_top > 0) ? TOP_FLAG : 0;
 
     // every slot starts on the gen stack with nothing to accumulate
     for (int k = lane; k < POOL; k += 32) {
@@ -221,7 +214,7 @@ __global__ void __launch_bounds__(RENDER_TPB, P::BLOCKS_PER_SM) k_render_pool(co
                 pre = P::pre(ray);
                 best.t = P::inf();
                 best.ref = -1;
-                cur = root;
+                cur = 0;
                 sp = 0;
             }
             tq_n -= take;
@@ -365,7 +358,7 @@ __global__ void __launch_bounds__(RENDER_TPB, P::BLOCKS_PER_SM) k_render_pool(co
             do {
 #pragma unroll
                 for (int u = 0; u < NODE_UNROLL; ++u) // node visits between two continue-votes
-                    if (cur >= 0) node_step<COUNT_RAYS, STAGE_TOP>(nodes, pre, P::t_min_f(), P::t_max_f(best), cur, sp, stack, tc, top);
+                    if (cur >= 0) wide_step<COUNT_RAYS>(wnodes, pre, P::t_min_f(), P::t_max_f(best), cur, sp, stack, tc);
             } while (++it < a.step_iters && __popc(__ballot_sync(0xffffffffu, cur >= 0)) >= a.th_node);
             const bool at_leaf = cur < 0 && cur != TRAV_DONE;
             const unsigned leaf_mask = __ballot_sync(0xffffffffu, at_leaf);

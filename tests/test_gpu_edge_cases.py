@@ -164,23 +164,66 @@ def test_python_rrt_class_mirror(built_lib):
     assert fb[-1].mean() > fb[0].mean() * 0.5  # row 0 is the BOTTOM scanline (ground), the top rows see sky
 
 
-def test_tree_top_staging_option_gives_the_same_image(ctx, monkeypatch):
-    """RRTB_STAGE_TOP=1 stages the breadth-first top of the LBVH in shared memory (north_star option; off by
-    default because it measured slower on B200, profiles/README.md): the image must not change."""
+def check_wide_tree(ctx, n_prims):
+    """The 4-wide traversal tree is a partition of the primitives: every sorted position is the leaf child of exactly
+    one node, every node but the root is the child of exactly one earlier node, and every child box (centre +- half
+    extent) encloses the canonical boxes of everything below it."""
+    w = ctx.wide_arrays()
+    b = ctx.bvh_arrays()
+    ref, c, h = w["ref"], w["c"], w["h"]
+    m = len(ref)
+    wd = ref.shape[1]
+    assert 1 <= m <= max(n_prims - 1, 1)
+    used = h[:, 0, :] > -np.inf
+    assert np.all(ref[~used] == np.int32(-2**31))
+    leaf = used & (ref < 0)
+    node = used & (ref >= 0)
+    slots = (~ref[leaf]) >> 2
+    assert np.array_equal(np.sort(slots), np.arange(n_prims))  # each primitive exactly once
+    kids = ref[node]
+    assert np.array_equal(np.sort(kids), np.arange(1, m))  # each node but the root exactly once
+    parent_of = np.zeros(m, np.int64)
+    rows = np.nonzero(node)[0]
+    parent_of[kids] = rows
+    assert np.all(parent_of[1:] < np.arange(1, m))  # parents are created first
+    # boxes: bottom-up union of the canonical primitive boxes, then containment in the stored child box
+    lo = np.full((m, 3), np.inf)
+    hi = np.full((m, 3), -np.inf)
+    pb = b["prim_box"][b["perm"]].astype(np.float64)  # sorted-position order
+    for i in range(m - 1, -1, -1):
+        for k in range(wd):
+            if not used[i, k]:
+                continue
+            if ref[i, k] < 0:
+                blo, bhi = pb[(~ref[i, k]) >> 2, :3], pb[(~ref[i, k]) >> 2, 3:]
+            else:
+                blo, bhi = lo[ref[i, k]], hi[ref[i, k]]
+            clo = c[i, :, k].astype(np.float64) - h[i, :, k].astype(np.float64)
+            chi = c[i, :, k].astype(np.float64) + h[i, :, k].astype(np.float64)
+            assert np.all(clo <= blo) and np.all(chi >= bhi), (i, k)
+            lo[i] = np.minimum(lo[i], blo)
+            hi[i] = np.maximum(hi[i], bhi)
+    types = (~ref[leaf]) & 3
+    return m, wd
+
+
+def test_wide_tree_is_a_partition_with_enclosing_boxes(ctx):
     from conftest import load_golden
 
-    scene, _ = load_golden("final")
-    ctx.set_scene(scene, use_bvh=True)
-    a, _ = ctx.render(96, 64, 6, 50, seed=11)
-    monkeypatch.setenv("RRTB_STAGE_TOP", "1")
-    b, _ = ctx.render(96, 64, 6, 50, seed=11)
-    assert a.tobytes() == b.tobytes()
-    tiny = make_scene(spheres=[((0, 0.5, 0), 1.0, 0)])  # single primitive: degenerate one-node tree
-    ctx.set_scene(tiny)
-    c, _ = ctx.render(32, 24, 2, 50, seed=1)
-    monkeypatch.delenv("RRTB_STAGE_TOP")
-    d, _ = ctx.render(32, 24, 2, 50, seed=1)
-    assert c.tobytes() == d.tobytes()
+    for name in ("final", "test2", "test3"):
+        scene, _ = load_golden(name)
+        ctx.set_scene(scene, use_bvh=True)
+        m, wd = check_wide_tree(ctx, scene.n_objects)
+        assert wd == 2 or m <= (scene.n_objects + 1) // 2 + 1 or scene.n_objects < 8  # the collapse about halves the node count
+    for n in (1, 2, 3, 4, 5):  # degenerate trees: fewer primitives than a node has slots
+        scene = make_scene(spheres=[((2.0 * k, 0.5, 0), 0.5, 0) for k in range(n)])
+        ctx.set_scene(scene)
+        m, wd = check_wide_tree(ctx, n)
+        assert m == (max(n - 1, 1) if wd == 2 else (1 if n <= 4 else 2))
+        a, _ = ctx.render(32, 24, 2, 50, seed=1)
+        ctx.set_scene(scene, use_bvh=False)
+        b2, _ = ctx.render(32, 24, 2, 50, seed=1)
+        assert a.tobytes() == b2.tobytes()
 
 
 def test_double_framebuffer_is_the_same_image(ctx, tmp_path, built_lib):
