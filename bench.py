@@ -8,15 +8,16 @@ Workload (BASELINE.json configs[1]): scenes/final.txt (488 spheres), 1200x800, 5
 A step = one full render of that image: 480 M camera paths, ~1.21 G ray segments.
 metric = Mrays/s = ray segments (closest-hit queries issued by the bounce loop) / seconds / 1e6.
 
-  value     device-resident: scene + LBVH already in HBM; a step = zero accumulator + render kernel
-            (+ NCCL reduce of the 64-bit accumulators to rank 0 when N > 1) + fixed-point resolve.
+  value     device-resident: scene + LBVH already in HBM; a step = zero accumulator + render kernel + the resolve
+            epilogue (N > 1: every rank's epilogue stores its tiles as float3 into rank 0's frame over NVLink).
   e2e       through the reference-facing C ABI with HOST buffers: rrtb_scene_set (H2D scene + LBVH build)
             + rrtb_render (render + resolve + D2H framebuffer) inside the timed region, every step.
   roofline  FP32-issue roofline of the render kernel: achieved = rays/s x W_ray lane-instr
             per ray (algorithmic count from the counting build's V_box, V_sph, ... on this very workload)
             against the issue rate MEASURED on this device by rrtb_probe_issue_rate.
-  N > 1     the image is split by interleaved 8x4 tiles (strong scaling: total work fixed), one process
-            per GPU, accumulators summed with one NCCL reduce (integers: order-independent, bit-identical).
+  N > 1     the image is split by interleaved 8x4 tiles (strong scaling: total work fixed), one process per GPU;
+            rank 0 owns the frame, the others map it once (CUDA IPC) and write their tiles into it from the resolve
+            kernel (rrtb_render_shard): 12 B/pixel/N over NVLink, no reduce.  torch.distributed = handle + barriers.
 """
 import argparse
 import json
@@ -89,10 +90,14 @@ def final_scene():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms DURING the timed region."""
+    """nvidia-smi clocks + throttle reasons sampled every 50 ms DURING the timed region.  The sampler is started before the
+    warm-up steps (nvidia-smi needs a few hundred ms to produce its first line) and every line carries nvidia-smi's own
+    timestamp; stop(t0, t1) keeps the samples taken inside the timed region [t0, t1] (wall-clock seconds), widened by one
+    poll period on each side so that a region shorter than a poll still has its bracketing samples."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    POLL_MS = 50
 
     def __init__(self, device):
         self.device = device
@@ -102,7 +107,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", str(self.POLL_MS)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -113,18 +118,32 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    @staticmethod
+    def _stamp(text):
+        import datetime
+
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0=None, t1=None):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(2 * self.POLL_MS * 1e-3)  # let the line that brackets the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
+        margin = self.POLL_MS * 1e-3
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
+                continue
+            ts = self._stamp(f[0])
+            if t0 is not None and ts is not None and not (t0 - margin <= ts <= t1 + margin):
                 continue
             try:
                 sm.append(float(f[1]))
@@ -137,7 +156,16 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None,
+                "poll_ms": self.POLL_MS, "lines_total": len(self.lines)}
+
+
+# Algorithmic work per ray segment of each workload ON THE CANONICAL BINARY LBVH (the structure whose codes, order and
+# topology are pinned bit-exactly against the oracle), measured once by the round-1 counting build
+# (profiles/r01_bench_*.json).  The roofline numerator uses THIS figure, so that a better traversal structure (the
+# 4-wide collapse, ...) raises the fraction instead of shrinking its own yardstick; the work actually traversed by the
+# current structure is reported beside it as `w_ray_traversed`.
+W_RAY_CANONICAL = {"final": 566.214, "synthetic": 1671.254, "test2": 293.815, "test3": 177.419}
 
 
 def w_ray(st):
@@ -213,27 +241,40 @@ def run_reference(args, rank):
 
 
 def reference_gpu_baseline(spp=50):
-    """The reference's own rrt.cu rebuilt for sm_100a (oracle/_ref/rrt), timed in the same run on the same
-    scene at a bounded spp (its cost is linear in spp).  Not an optimisation target."""
+    """The reference's own rrt.cu rebuilt for sm_100a (oracle/_ref/rrt), timed in the same run on the same scene: the
+    block shapes of BASELINE.md section 3 (the reference's PERFORMANCE.txt:6-19 has wide flat blocks as its fastest)
+    at a bounded spp (its cost is linear in spp), then the best shape once at the full 500 spp.  Not an optimisation
+    target."""
     exe = os.path.join(ROOT, "oracle", "_ref", "rrt")
     scene_txt = os.path.join(ROOT, "oracle", "_ref", "scenes", "final.txt")
     if not (os.path.exists(exe) and os.path.exists(scene_txt)):
         return None
-    best = None
-    for tx, ty in ((8, 8), (16, 16), (128, 2)):
+
+    def run(tx, ty, n_spp):
         try:
-            r = subprocess.run([exe, "-i", scene_txt, "-w", str(W), "-h", str(H), "-s", str(spp), "-d", str(DEPTH), "-tx", str(tx), "-ty", str(ty), "-o", "/tmp/_rrt_ref.png"],
+            r = subprocess.run([exe, "-i", scene_txt, "-w", str(W), "-h", str(H), "-s", str(n_spp), "-d", str(DEPTH), "-tx", str(tx), "-ty", str(ty), "-o", "/tmp/_rrt_ref.png"],
                                capture_output=True, text=True, timeout=600)
         except Exception:
-            continue
+            return None
         for ln in r.stderr.splitlines():
             if ln.startswith("stats,"):
-                sec = float(ln.split(",")[-1])
-                if best is None or sec < best[0]:
-                    best = (sec, tx, ty)
-    if best is None:
+                return float(ln.split(",")[-1])
         return None
-    return {"seconds": best[0], "spp": spp, "block": "%dx%d" % (best[1], best[2])}
+
+    sweep = {}
+    for tx, ty in ((8, 8), (16, 16), (128, 2), (256, 1), (512, 1)):
+        sec = run(tx, ty, spp)
+        if sec is not None:
+            sweep["%dx%d" % (tx, ty)] = sec
+    if not sweep:
+        return None
+    block = min(sweep, key=sweep.get)
+    out = {"seconds": sweep[block], "spp": spp, "block": block, "sweep_seconds_at_%d_spp" % spp: sweep}
+    tx, ty = (int(x) for x in block.split("x"))
+    full = run(tx, ty, SPP)
+    if full is not None:
+        out["seconds_at_500_spp"] = full
+    return out
 
 
 def cpu_baseline_sample(rays_per_path):
@@ -423,17 +464,24 @@ def main():
 
     kernel_seconds = []
 
+    dr = None
+    if world > 1:  # rank 0 owns the frame, the others map it (CUDA IPC); see rrt_b200/dist.py
+        from rrt_b200.dist import DistributedRenderer
+
+        dr = DistributedRenderer(ctx, rank, world)
+        dr.ensure_frame(Wl, Hl, f64)
+
     def step():
         flush.fill_(1.0)  # L2 flush between timed iterations (the scene itself is far smaller than L2)
-        acc.zero_()
-        torch.cuda.synchronize()  # ctx renders on its own stream
-        st = ctx.render_device(params, acc.data_ptr())
-        kernel_seconds.append(st["seconds_render"])
-        if world > 1:
-            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
-            torch.cuda.synchronize()
-        if rank == 0:
+        if world == 1:
+            acc.zero_()
+            torch.cuda.synchronize()  # ctx renders on its own stream
+            st = ctx.render_device(params, acc.data_ptr())
             ctx.resolve_device(acc.data_ptr(), out.data_ptr(), n)
+        else:
+            torch.cuda.synchronize()
+            st = ctx.render_shard(params)  # zero own accumulator + render + epilogue into rank 0's frame over NVLink
+        kernel_seconds.append(st["seconds_render"])
 
     # counting pass (untimed): rays and per-ray work of exactly this workload and shard
     pc = ctx.params(Wl, Hl, spp, DEPTH, SEED, rank, world, shard_mode, True, precision=args.precision)
@@ -447,13 +495,14 @@ def main():
     tot = dict(zip(("rays", "box_tests", "sphere_tests", "msphere_tests", "triangle_tests", "hits", "paths"), counts.tolist()))
     total_rays = tot["rays"]
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # before the warm-up: nvidia-smi is up and printing by the time the timed region starts
     for _ in range(args.warmup):
         step()
     kernel_seconds.clear()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
+    wall0 = time.time()
     t0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -463,7 +512,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     dev_s = ev0.elapsed_time(ev1) * 1e-3
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall0 + wall) if rank == 0 else None
     # max over ranks of the device-timed region
     tt = torch.tensor([dev_s, wall, sum(kernel_seconds) / len(kernel_seconds)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -472,24 +521,25 @@ def main():
     sec_per_step = dev_s / args.steps
     value = total_rays / sec_per_step / 1e6
 
-    # ---- e2e: through the C ABI with host buffers, every step: scene upload + LBVH build + render + D2H
-    host_out = np.empty((Hl, Wl, 3), np.float64 if f64 else np.float32)
+    # ---- e2e: through the C ABI with HOST buffers, every step: scene upload + LBVH build + render + D2H of the frame
+    from rrt_b200 import PinnedBuffer
+
+    pin = PinnedBuffer((Hl, Wl, 3), np.float64 if f64 else np.float32) if rank == 0 else None  # pinned: the D2H is one DMA
+    host_out = pin.array if rank == 0 else None
     h2d = scene.camera.nbytes + scene.materials.nbytes + scene.spheres.nbytes + scene.mspheres.nbytes + scene.triangles.nbytes
     d2h = host_out.nbytes if rank == 0 else 0
 
     def e2e_step():
-        ctx.set_scene(scene, use_bvh=True)
         if world == 1:
+            ctx.set_scene(scene, use_bvh=True)
             ctx.render(Wl, Hl, spp, DEPTH, SEED, out=host_out, precision=args.precision)
         else:
-            acc.zero_()
-            torch.cuda.synchronize()
-            ctx.render_device(params, acc.data_ptr())
-            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
-            torch.cuda.synchronize()
+            dist.barrier()  # rank 0 has read the previous frame
+            ctx.set_scene(scene, use_bvh=True)
+            ctx.render_shard(params)
+            dist.barrier()  # every rank's tiles are in rank 0's frame
             if rank == 0:
-                ctx.resolve_device(acc.data_ptr(), out.data_ptr(), n)
-                host_out.reshape(-1)[:] = out.cpu().numpy()
+                ctx.frame_download(host_out, shard_mode)
 
     e2e_step()
     barrier()
@@ -504,14 +554,17 @@ def main():
     e2e_value = total_rays / (e2e_t.item() / e2e_steps) / 1e6
 
     if rank == 0:
-        wr, v = w_ray(tot)
+        wr_trav, v = w_ray(tot)
+        wr = W_RAY_CANONICAL.get(args.workload, wr_trav) if (Wl, Hl) == (wl["W"], wl["H"]) else wr_trav
         probe = ctx.probe_issue_rate()
+        info = ctx.device_info()
+        nominal = info["sm_count"] * 128 * info["clock_khz"] * 1e3  # lanes x clock: 1 warp-instruction / clk / SM sub-partition
         kern_rays_per_s = (cst["rays"] if world == 1 else tot["rays"] / world) / kern_s
         achieved = kern_rays_per_s * wr  # lane-instr / s, per GPU
         peak = max(probe["ffma"], probe["ffma_fmnmx_mix"])  # the issue-rate ceiling: 1 warp-instr / clk / SMSP
         traffic = None  # dram bytes per launch of the render kernel, from the committed ncu --set full capture
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
                 traffic = json.load(f)["traffic_bytes_per_launch"] if (headline and world == 1) else None
         except Exception:
             pass
@@ -521,15 +574,18 @@ def main():
             "dtype": "f64 (float slab tests, u64 fixed-point accumulation)" if f64 else "f32 (f64 leaf discriminants, u64 fixed-point accumulation)",
             "data": "%s (%s)" % (wl["data"], scene_src),
             "config": {"workload": "%s %dx%d, %d spp, depth 50 (%s)" % (wl["label"], Wl, Hl, spp, wl["config"]), "prims": scene.n_objects,
-                       "sharding": "one image, %s over %d GPU(s), NCCL reduce of u64 accumulators" % ("interleaved 8x4 tiles" if shard_mode == 0 else "interleaved samples", world),
+                       "sharding": "one image, %s over %d GPU(s); %s" % ("interleaved 8x4 tiles" if shard_mode == 0 else "interleaved samples", world,
+                                                                         "single GPU" if world == 1 else ("each rank's resolve kernel stores its tiles as float3 into rank 0's frame over NVLink (CUDA IPC peer mapping): %d bytes per frame cross the link" % (12 * Wl * Hl * (world - 1) // world) if shard_mode == 0 else "each rank adds its u64 partial sums into rank 0's buffer over NVLink (integer atomics)")),
                        "l2": "256 MiB flush written between timed iterations", "rays_per_step": total_rays,
                        "rays_per_path": total_rays / tot["paths"], **{k: round(x, 4) for k, x in v.items()}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": "rrtb_scene_set (upload + LBVH build) + rrtb_render (render + resolve + D2H) per step"},
+                    "what": "rrtb_scene_set (upload + LBVH build + 4-wide collapse) + " + ("rrtb_render (render + resolve + D2H into pinned host memory)" if world == 1 else "rrtb_render_shard on every rank + 2 barriers + rrtb_frame_download on rank 0 (pinned host memory)") + " per step"},
             "gpu_launches": args.steps * 2,
-            "kernel": {"name": "rrtb::k_render_f64<true,false>" if f64 else "rrtb::k_render_pool<false>", "avg_ms": kern_s * 1e3, "share_of_step": kern_s / sec_per_step},
+            "kernel": {"name": "rrtb::k_render_pool<false,2,true,PathF64>" if f64 else "rrtb::k_render_pool<false,2,false,PathF32>", "avg_ms": kern_s * 1e3, "share_of_step": kern_s / sec_per_step},
             "roofline": {"bound": "fp32_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T lane-instr/s",
-                         "frac": achieved / peak, "traffic": traffic, "w_ray": wr,
+                         "frac": achieved / peak, "frac_nominal": achieved / nominal, "peak_nominal": nominal / 1e12, "traffic": traffic, "w_ray": wr,
+                         "w_ray_traversed": wr_trav,
+                         "w_ray_note": "w_ray = algorithmic lane-instructions per ray segment on the canonical binary LBVH (round-1 counting build, fixed per workload); w_ray_traversed = the same cost model over what the current 4-wide tree visits",
                          "peak_source": "measured on this device by rrtb_probe_issue_rate: FFMA-only loop %.2f T lane-instr/s (an FFMA+FMNMX "
                                         "slab-test mix reaches %.2f); nominal 148 SM x 128 lanes x 1.965 GHz = 37.2; MEASURED_PEAKS.json "
                                         "has no FP32 figure" % (probe["ffma"] / 1e12, probe["ffma_fmnmx_mix"] / 1e12),
@@ -544,7 +600,9 @@ def main():
             g = reference_gpu_baseline()
             if g:
                 g["Mrays/s"] = W * H * g["spp"] * (total_rays / tot["paths"]) / g["seconds"] / 1e6
-                g["what"] = "reference rrt.cu rebuilt for sm_100a (oracle/_ref/rrt), float, its own BVH, best of 3 block shapes"
+                if "seconds_at_500_spp" in g:
+                    g["Mrays/s_at_500_spp"] = W * H * SPP * (total_rays / tot["paths"]) / g["seconds_at_500_spp"] / 1e6
+                g["what"] = "reference rrt.cu rebuilt for sm_100a (oracle/_ref/rrt), float, its own BVH, best of 5 block shapes at 50 spp, then that shape at 500 spp"
                 line["reference_gpu"] = g
         else:
             line["cpu_baseline"] = None

@@ -137,8 +137,9 @@ enum { RRTB_SHARD_TILES = 0, RRTB_SHARD_SAMPLES = 1 };
 enum { RRTB_SCHED_AUTO = 0, RRTB_SCHED_SIMPLE = 1, RRTB_SCHED_POOL = 2 };
 /* arithmetic of the integrator = the reference's two builds (rtweekend.h:20-28, Makefile:32-37):
  *   RRTB_PRECISION_F32  `rrt`  (-DUSE_FLOAT): float rays / shading, intersection kernels exact to 2.2e-6 (default)
- *   RRTB_PRECISION_F64  `rrtd` (FP_T = double): rays, hit points, normals, scattering and throughput in double;
- *                       persistent one-path-per-lane kernel whatever `scheduler` says.  Same Philox streams. */
+ *   RRTB_PRECISION_F64  `rrtd` (FP_T = double): rays, hit points, normals, scattering and throughput in double, on
+ *                       the same pool scheduler (RRTB_SCHED_SIMPLE and the flat scan: one path per lane).  Same
+ *                       Philox streams. */
 enum { RRTB_PRECISION_F32 = 0, RRTB_PRECISION_F64 = 1 };
 
 typedef struct rrtb_render_params {
@@ -186,6 +187,40 @@ int rrtb_render_device(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_a
 int rrtb_resolve_device(rrtb_ctx *ctx, const uint64_t *d_accum, float *d_out_rgb, size_t n);
 /* sum 64-bit accumulators: d_dst[k] += d_src[k] (device pointers; d_src may be a peer mapping) */
 int rrtb_accumulate_device(rrtb_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t n);
+
+/* ---- multi-GPU: ONE image over the GPUs of one box (NVLink 5 / NVSwitch) ---------------------------------------
+ * The reference renders on one device (`-D n`, main.cpp:107-110); BASELINE north_star asks for tile / sample
+ * sharding with the combine over NVLink.  Rank 0 (the OWNER) holds the frame.  Every rank renders its shard into
+ * its own accumulator, and its epilogue kernel then writes into the owner's memory directly:
+ *   RRTB_SHARD_TILES    the rank's tiles, resolved to 3 floats (or doubles) per pixel, STORED into the owner's frame:
+ *                       tiles are disjoint, so there is no reduction and no zero-fill; 12 B/pixel/world cross the link
+ *   RRTB_SHARD_SAMPLES  the rank's 64-bit partial sums ADDED into the owner's sum buffer (integer atomics: the image
+ *                       does not depend on arrival order); the owner resolves at download time
+ * Ranks > 0 reach the owner's memory through a peer mapping: rrtb_frame_attach inside one process (the drop-in's
+ * `-G n`), rrtb_frame_export -> (any byte transport, e.g. a torch.distributed broadcast) -> rrtb_frame_import across
+ * processes (one process per GPU).  The caller orders the phases: all ranks' rrtb_render_shard have returned (a
+ * barrier between processes) before the owner's rrtb_frame_download, and the download has returned before the next
+ * frame's shards are rendered. */
+#define RRTB_FRAME_HANDLE_BYTES 192
+/* owner: allocate (or re-use) the frame for width x height; frame_f64 != 0 = double sums (the `rrtd` framebuffer) */
+int rrtb_frame_create(rrtb_ctx *ctx, int width, int height, int frame_f64);
+int rrtb_frame_export(rrtb_ctx *ctx, void *handle /* RRTB_FRAME_HANDLE_BYTES */);
+int rrtb_frame_import(rrtb_ctx *ctx, const void *handle);
+int rrtb_frame_attach(rrtb_ctx *ctx, rrtb_ctx *owner); /* same process; enables peer access ctx -> owner */
+int rrtb_frame_detach(rrtb_ctx *ctx);
+/* render shard (p->rank, p->world, p->shard_mode) and run the epilogue into the owner's frame; returns when this
+ * rank's stores have landed */
+int rrtb_render_shard(rrtb_ctx *ctx, const rrtb_render_params *p, rrtb_stats *stats);
+/* owner: frame -> host (3*W*H floats, or doubles for an f64 frame).  A destination from rrtb_host_alloc is written
+ * by DMA directly; a pageable one goes through pinned staging. */
+int rrtb_frame_download(rrtb_ctx *ctx, int shard_mode, void *out_rgb);
+/* One process driving n devices (`rrt -G n`): ctxs[0] owns the frame, every context has the scene loaded; all shards
+ * are enqueued before any is waited for.  p->rank / p->world are ignored (rank i = ctxs[i], world = n). */
+int rrtb_render_group(rrtb_ctx *const *ctxs, int n, const rrtb_render_params *p, int frame_f64, void *out_rgb,
+                      rrtb_stats *stats);
+/* Pinned (page-locked, portable) host memory for framebuffers and scene arrays: copies to and from it are DMA. */
+void *rrtb_host_alloc(size_t bytes);
+void rrtb_host_free(void *p);
 
 /* Measurement aid (no reference counterpart): the FP32-issue roofline denominator measured on
  * THIS device -- lane-instructions per second of an FFMA-only loop and of an FFMA+FMNMX (slab-test) mix. */

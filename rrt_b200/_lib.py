@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("RRTB_LIB") or os.path.join(_HERE, "librrtb200.so")  #
 SYMBOLS = [
     "rrtb_abi_version", "rrtb_create", "rrtb_destroy", "rrtb_last_error", "rrtb_device_info",
     "rrtb_scene_set", "rrtb_scene_stage_moving_triangles", "rrtb_camera_set", "rrtb_render", "rrtb_render_f64", "rrtb_render_device", "rrtb_resolve_device",
-    "rrtb_accumulate_device", "rrtb_trace_closest", "rrtb_trace_closest_f64", "rrtb_camera_rays", "rrtb_camera_rays_f64",
+    "rrtb_accumulate_device", "rrtb_frame_create", "rrtb_frame_export", "rrtb_frame_import", "rrtb_frame_attach", "rrtb_frame_detach",
+    "rrtb_render_shard", "rrtb_frame_download", "rrtb_render_group", "rrtb_host_alloc", "rrtb_host_free", "rrtb_trace_closest", "rrtb_trace_closest_f64", "rrtb_camera_rays", "rrtb_camera_rays_f64",
     "rrtb_bvh_size", "rrtb_bvh_download", "rrtb_wide_size", "rrtb_wide_download", "rrtb_philox", "rrtb_scatter", "rrtb_scatter_f64", "rrtb_probe_issue_rate", "rrtb_scene_parse_file", "rrtb_scene_free", "rrtb_scene_counts",
     "rrtb_scene_camera", "rrtb_scene_materials", "rrtb_scene_spheres", "rrtb_scene_mspheres",
     "rrtb_scene_triangles", "rrtb_scene_mtriangle_count", "rrtb_scene_mtriangles", "rrtb_scene_upload", "rrtb_camera_derive", "rrtb_tonemap_rgb8", "rrtb_tonemap_rgb8_f64", "rrtb_write_png",
@@ -60,6 +61,16 @@ def load():
         "rrtb_render_device": (C.c_int, [vp, P(RenderParams), vp, P(Stats)]),
         "rrtb_resolve_device": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "rrtb_accumulate_device": (C.c_int, [vp, vp, vp, C.c_size_t]),
+        "rrtb_frame_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
+        "rrtb_frame_export": (C.c_int, [vp, vp]),
+        "rrtb_frame_import": (C.c_int, [vp, vp]),
+        "rrtb_frame_attach": (C.c_int, [vp, vp]),
+        "rrtb_frame_detach": (C.c_int, [vp]),
+        "rrtb_render_shard": (C.c_int, [vp, P(RenderParams), P(Stats)]),
+        "rrtb_frame_download": (C.c_int, [vp, C.c_int, vp]),
+        "rrtb_render_group": (C.c_int, [P(vp), C.c_int, P(RenderParams), C.c_int, vp, P(Stats)]),
+        "rrtb_host_alloc": (vp, [C.c_size_t]),
+        "rrtb_host_free": (None, [vp]),
         "rrtb_trace_closest": (C.c_int, [vp, vp, C.c_int, f32, C.c_int, vp, vp, vp]),
         "rrtb_camera_rays": (C.c_int, [vp, P(RenderParams), vp, C.c_int, C.c_int, vp]),
         "rrtb_trace_closest_f64": (C.c_int, [vp, vp, C.c_int, C.c_double, C.c_int, vp, vp, vp]),

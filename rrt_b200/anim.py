@@ -33,14 +33,14 @@ def frames_of_rank(n_frames, rank, world):
     return list(range(rank, n_frames, max(world, 1)))
 
 
-def render_frames(ctx, cameras, width, height, spp, max_depth=50, seed=1984, rank=0, world=1, on_frame=None):
+def render_frames(ctx, cameras, width, height, spp, max_depth=50, seed=1984, rank=0, world=1, on_frame=None, count_rays=False):
     """Render this rank's frames of a camera-only animation with ONE uploaded scene (ctx.set_scene first).
     on_frame(index, image[H, W, 3] float32 sums, stats) is called per frame; returns summed stats."""
     total = dict(frames=0, rays=0, paths=0, seconds_render=0.0)
     out = np.empty((height, width, 3), np.float32)
     for f in frames_of_rank(len(cameras), rank, world):
         ctx.set_camera(cameras[f])
-        img, st = ctx.render(width, height, spp, max_depth, seed, count_rays=on_frame is None or True, out=out)
+        img, st = ctx.render(width, height, spp, max_depth, seed, count_rays=count_rays, out=out)
         total["frames"] += 1
         total["rays"] += st["rays"]
         total["paths"] += st["paths"]

@@ -106,6 +106,49 @@ class Scene:
 
 
 _PRECISION = {"f32": 0, "f64": 1, 0: 0, 1: 1}
+FRAME_HANDLE_BYTES = 192  # RRTB_FRAME_HANDLE_BYTES
+
+
+def render_group(contexts, width, height, spp, max_depth=50, seed=1984, shard_mode=0, out=None, dtype=np.float32, precision="f32",
+                 count_rays=False):
+    """One process, n GPUs (the drop-in's `-G n`): contexts[0] owns the frame, every context has the scene loaded;
+    shard i of len(contexts) renders on contexts[i] and lands in the owner's frame over NVLink."""
+    lib = contexts[0].lib
+    dtype = np.dtype(dtype) if out is None else out.dtype
+    if out is None:
+        out = np.empty((height, width, 3), dtype)
+    p = Context.params(width, height, spp, max_depth, seed, 0, len(contexts), shard_mode, count_rays, 0, precision)
+    hs = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    st = Stats()
+    rc = lib.rrtb_render_group(hs, len(contexts), C.byref(p), 1 if dtype == np.dtype(np.float64) else 0, C.c_void_p(out.ctypes.data), C.byref(st))
+    if rc != 0:
+        raise RrtbError(rc, lib.rrtb_last_error(contexts[0].h).decode())
+    return out, st.as_dict()
+
+
+class PinnedBuffer:
+    """Page-locked host memory from rrtb_host_alloc as a numpy array (`.array`): device copies to / from it are DMA."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.lib = _lib.load()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        self.ptr = self.lib.rrtb_host_alloc(n)
+        if not self.ptr:
+            raise MemoryError("rrtb_host_alloc(%d)" % n)
+        self.array = np.frombuffer((C.c_char * n).from_address(self.ptr), dtype=dtype).reshape(shape)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self.lib.rrtb_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class Context:
@@ -204,6 +247,40 @@ class Context:
 
     def accumulate_device(self, dst_ptr, src_ptr, n):
         self._check(self.lib.rrtb_accumulate_device(self.h, C.c_void_p(int(dst_ptr)), C.c_void_p(int(src_ptr)), int(n)))
+
+    # -- multi-GPU frame (include/rrtb.h "multi-GPU") -----------------------------------------------------
+    def frame_create(self, width, height, f64=False):
+        """Owner (rank 0): the frame every rank's epilogue writes its shard into."""
+        self._check(self.lib.rrtb_frame_create(self.h, int(width), int(height), 1 if f64 else 0))
+
+    def frame_export(self):
+        """Owner: the bytes another PROCESS needs to map the frame (rrtb_frame_import)."""
+        buf = C.create_string_buffer(FRAME_HANDLE_BYTES)
+        self._check(self.lib.rrtb_frame_export(self.h, buf))
+        return buf.raw
+
+    def frame_import(self, handle):
+        assert len(handle) == FRAME_HANDLE_BYTES
+        self._check(self.lib.rrtb_frame_import(self.h, C.create_string_buffer(bytes(handle), FRAME_HANDLE_BYTES)))
+
+    def frame_attach(self, owner):
+        """Same process: peer access to the owner context's frame."""
+        self._check(self.lib.rrtb_frame_attach(self.h, owner.h))
+
+    def frame_detach(self):
+        self._check(self.lib.rrtb_frame_detach(self.h))
+
+    def render_shard(self, params):
+        """Render shard (params.rank, params.world) and store / add it into the owner's frame."""
+        st = Stats()
+        self._check(self.lib.rrtb_render_shard(self.h, C.byref(params), C.byref(st)))
+        return st.as_dict()
+
+    def frame_download(self, out, shard_mode=0):
+        """Owner: frame -> host array `out` ([H, W, 3] float32, or float64 for an f64 frame)."""
+        assert out.flags.c_contiguous
+        self._check(self.lib.rrtb_frame_download(self.h, int(shard_mode), C.c_void_p(out.ctypes.data)))
+        return out
 
     # -- test hooks -------------------------------------------------------------------------------------
     def trace(self, rays7, t_min=0.001, mode="bvh", want_rec=False):

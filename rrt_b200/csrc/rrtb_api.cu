@@ -103,6 +103,8 @@ int rrtb_create(rrtb_ctx **out, int device)
     CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CREATE_CUDA(cudaEventCreate(&ctx->ev0));
     CREATE_CUDA(cudaEventCreate(&ctx->ev1));
+    CREATE_CUDA(cudaEventCreate(&ctx->ev2));
+    CREATE_CUDA(cudaEventCreate(&ctx->ev3));
     CREATE_CUDA(cudaMalloc((void **)&ctx->d_counters, 8 * sizeof(unsigned long long)));
 #undef CREATE_CUDA
     *out = ctx;
@@ -117,8 +119,15 @@ void rrtb_destroy(rrtb_ctx *ctx)
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_accum) cudaFree(ctx->d_accum);
     if (ctx->d_rgb) cudaFree(ctx->d_rgb);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->peer_is_ipc) {
+        if (ctx->peer_frame) cudaIpcCloseMemHandle(ctx->peer_frame);
+        if (ctx->peer_sum) cudaIpcCloseMemHandle(ctx->peer_sum);
+    }
+    if (ctx->d_frame) cudaFree(ctx->d_frame);
+    if (ctx->d_sum) cudaFree(ctx->d_sum);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev2, ctx->ev3, ctx->ev_copy[0], ctx->ev_copy[1]})
+        if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -282,6 +291,61 @@ int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam)
     return RRTB_OK;
 }
 
+// Device -> host copy of a result.  A pinned destination (rrtb_host_alloc, cudaHostRegister) is written by DMA
+// directly; a pageable one is fed through two pinned 4 MB halves so that the copy engine and the host memcpy overlap
+// (a plain cudaMemcpy into pageable memory serialises the two).
+static int copy_to_host(rrtb_ctx *ctx, void *dst, const void *d_src, size_t bytes)
+{
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        RRTB_CUDA(ctx, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return RRTB_OK;
+    }
+    const size_t CH = (size_t)4 << 20;
+    if (!ctx->h_pinned) {
+        RRTB_CUDA(ctx, cudaHostAlloc(&ctx->h_pinned, 2 * CH, cudaHostAllocPortable));
+        ctx->h_pinned_bytes = 2 * CH;
+    }
+    if (!ctx->ev_copy[0]) {
+        RRTB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[0], cudaEventDisableTiming));
+        RRTB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[1], cudaEventDisableTiming));
+    }
+    const size_t n_chunks = (bytes + CH - 1) / CH;
+    for (size_t k = 0; k <= n_chunks; ++k) {
+        if (k < n_chunks) {
+            if (k >= 2) RRTB_CUDA(ctx, cudaEventSynchronize(ctx->ev_copy[k & 1])); // (its memcpy below is done too: same thread)
+            const size_t len = (k + 1 == n_chunks) ? bytes - k * CH : CH;
+            RRTB_CUDA(ctx, cudaMemcpyAsync((char *)ctx->h_pinned + (k & 1) * CH, (const char *)d_src + k * CH, len,
+                                           cudaMemcpyDeviceToHost, ctx->stream));
+            RRTB_CUDA(ctx, cudaEventRecord(ctx->ev_copy[k & 1], ctx->stream));
+        }
+        if (k >= 1) {
+            const size_t j = k - 1, len = (j + 1 == n_chunks) ? bytes - j * CH : CH;
+            RRTB_CUDA(ctx, cudaEventSynchronize(ctx->ev_copy[j & 1]));
+            memcpy((char *)dst + j * CH, (const char *)ctx->h_pinned + (j & 1) * CH, len);
+        }
+    }
+    return RRTB_OK;
+}
+
+// accumulator of the host / frame paths: grow-only, 3*W*H 64-bit sums
+static int reserve_accum(rrtb_ctx *ctx, size_t n)
+{
+    if (ctx->accum_elems >= n) return RRTB_OK;
+    if (ctx->d_accum) cudaFree(ctx->d_accum);
+    if (ctx->d_rgb) cudaFree(ctx->d_rgb);
+    ctx->d_accum = nullptr;
+    ctx->d_rgb = nullptr;
+    ctx->accum_elems = 0;
+    RRTB_CUDA(ctx, cudaMalloc((void **)&ctx->d_accum, n * sizeof(unsigned long long)));
+    RRTB_CUDA(ctx, cudaMalloc((void **)&ctx->d_rgb, n * sizeof(double))); // room for the f64 resolve too
+    ctx->accum_elems = n;
+    return RRTB_OK;
+}
+
 static int check_render(rrtb_ctx *ctx, const rrtb_render_params *p)
 {
     if (!ctx || !p) return RRTB_ERR_INVALID;
@@ -292,7 +356,7 @@ static int check_render(rrtb_ctx *ctx, const rrtb_render_params *p)
     if (p->width < 2 || p->height < 2) return invalid(ctx, "image must be at least 2x2 (u = (i+xi)/(W-1), rrt.cu:112)");
     if (p->spp < 1 || p->max_depth < 0) return invalid(ctx, "spp must be >= 1 and max_depth >= 0");
     if ((long long)p->width * p->height >= (1ll << 28)) return invalid(ctx, "image too large (limit 2^28 pixels)");
-    if (p->world > 1 && (p->rank < 0 || p->rank >= p->world)) return invalid(ctx, "rank out of range");
+    if (p->rank < 0 || p->rank >= (p->world > 1 ? p->world : 1)) return invalid(ctx, "rank out of range (0 <= rank < max(world, 1))");
     if (p->shard_mode != RRTB_SHARD_TILES && p->shard_mode != RRTB_SHARD_SAMPLES) return invalid(ctx, "bad shard_mode");
     if (p->precision != RRTB_PRECISION_F32 && p->precision != RRTB_PRECISION_F64) return invalid(ctx, "bad precision");
     return RRTB_OK;
@@ -334,16 +398,7 @@ static int render_host(rrtb_ctx *ctx, const rrtb_render_params *p, void *out_rgb
     if (!out_rgb) return invalid(ctx, "null output buffer");
     RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)3 * p->width * p->height;
-    if (ctx->accum_elems < n) {
-        if (ctx->d_accum) cudaFree(ctx->d_accum);
-        if (ctx->d_rgb) cudaFree(ctx->d_rgb);
-        ctx->d_accum = nullptr;
-        ctx->d_rgb = nullptr;
-        ctx->accum_elems = 0;
-        RRTB_CUDA(ctx, cudaMalloc((void **)&ctx->d_accum, n * sizeof(unsigned long long)));
-        RRTB_CUDA(ctx, cudaMalloc((void **)&ctx->d_rgb, n * sizeof(double))); // room for the f64 resolve too
-        ctx->accum_elems = n;
-    }
+    if ((rc = reserve_accum(ctx, n))) return rc;
     RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_accum, 0, n * sizeof(unsigned long long), ctx->stream));
     rrtb_stats local;
     memset(&local, 0, sizeof(local));
@@ -354,8 +409,7 @@ static int render_host(rrtb_ctx *ctx, const rrtb_render_params *p, void *out_rgb
     rc = f64 ? launch_resolve_f64(ctx, (const uint64_t *)ctx->d_accum, (double *)ctx->d_rgb, n)
              : launch_resolve(ctx, (const uint64_t *)ctx->d_accum, ctx->d_rgb, n);
     if (rc) return rc;
-    RRTB_CUDA(ctx, cudaMemcpyAsync(out_rgb, ctx->d_rgb, n * (f64 ? sizeof(double) : sizeof(float)), cudaMemcpyDeviceToHost,
-                                   ctx->stream));
+    if ((rc = copy_to_host(ctx, out_rgb, ctx->d_rgb, n * (f64 ? sizeof(double) : sizeof(float))))) return rc;
     RRTB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
@@ -374,6 +428,248 @@ int rrtb_render(rrtb_ctx *ctx, const rrtb_render_params *p, float *out_rgb, rrtb
 int rrtb_render_f64(rrtb_ctx *ctx, const rrtb_render_params *p, double *out_rgb, rrtb_stats *stats)
 {
     return render_host(ctx, p, out_rgb, stats, true);
+}
+
+// ---- multi-GPU frame ---------------------------------------------------------------------------------
+namespace {
+struct FrameHandle { // what crosses the process boundary (RRTB_FRAME_HANDLE_BYTES)
+    cudaIpcMemHandle_t frame, sum;
+    int32_t width, height, f64, device;
+};
+static_assert(sizeof(FrameHandle) <= RRTB_FRAME_HANDLE_BYTES, "handle blob too small");
+} // namespace
+
+static void frame_drop_mapping(rrtb_ctx *ctx)
+{
+    if (ctx->peer_is_ipc) {
+        if (ctx->peer_frame) cudaIpcCloseMemHandle(ctx->peer_frame);
+        if (ctx->peer_sum) cudaIpcCloseMemHandle(ctx->peer_sum);
+    }
+    ctx->peer_frame = nullptr;
+    ctx->peer_sum = nullptr;
+    ctx->peer_is_ipc = false;
+}
+
+int rrtb_frame_create(rrtb_ctx *ctx, int width, int height, int frame_f64)
+{
+    if (!ctx) return RRTB_ERR_INVALID;
+    if (width < 2 || height < 2 || (long long)width * height >= (1ll << 28)) return invalid(ctx, "bad frame size");
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    frame_drop_mapping(ctx);
+    const size_t n = (size_t)3 * width * height;
+    if (ctx->frame_elems < n) { // cudaMalloc'ed directly (not sub-allocated): the pair must be exportable through CUDA IPC
+        if (ctx->d_frame) cudaFree(ctx->d_frame);
+        if (ctx->d_sum) cudaFree(ctx->d_sum);
+        ctx->d_frame = nullptr;
+        ctx->d_sum = nullptr;
+        ctx->frame_elems = 0;
+        RRTB_CUDA(ctx, cudaMalloc(&ctx->d_frame, n * sizeof(double)));
+        RRTB_CUDA(ctx, cudaMalloc((void **)&ctx->d_sum, n * sizeof(unsigned long long)));
+        ctx->frame_elems = n;
+    }
+    ctx->frame_w = width;
+    ctx->frame_h = height;
+    ctx->frame_f64 = frame_f64 ? 1 : 0;
+    RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_sum, 0, n * sizeof(unsigned long long), ctx->stream));
+    RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RRTB_OK;
+}
+
+int rrtb_frame_export(rrtb_ctx *ctx, void *handle)
+{
+    if (!ctx || !handle) return RRTB_ERR_INVALID;
+    if (!ctx->d_frame) return invalid(ctx, "rrtb_frame_export before rrtb_frame_create");
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    FrameHandle h;
+    memset(&h, 0, sizeof(h));
+    RRTB_CUDA(ctx, cudaIpcGetMemHandle(&h.frame, ctx->d_frame));
+    RRTB_CUDA(ctx, cudaIpcGetMemHandle(&h.sum, ctx->d_sum));
+    h.width = ctx->frame_w;
+    h.height = ctx->frame_h;
+    h.f64 = ctx->frame_f64;
+    h.device = ctx->device;
+    memset(handle, 0, RRTB_FRAME_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof(h));
+    return RRTB_OK;
+}
+
+int rrtb_frame_import(rrtb_ctx *ctx, const void *handle)
+{
+    if (!ctx || !handle) return RRTB_ERR_INVALID;
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    frame_drop_mapping(ctx);
+    FrameHandle h;
+    memcpy(&h, handle, sizeof(h));
+    if (h.width < 2 || h.height < 2) return invalid(ctx, "bad frame handle");
+    // peer mapping of the owner's allocations: loads and stores of this context's kernels go over NVLink
+    RRTB_CUDA(ctx, cudaIpcOpenMemHandle(&ctx->peer_frame, h.frame, cudaIpcMemLazyEnablePeerAccess));
+    void *sum = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&sum, h.sum, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaIpcCloseMemHandle(ctx->peer_frame);
+        ctx->peer_frame = nullptr;
+        return cuda_fail(ctx, e, "cudaIpcOpenMemHandle(sum)", __FILE__, __LINE__);
+    }
+    ctx->peer_sum = (unsigned long long *)sum;
+    ctx->peer_is_ipc = true;
+    ctx->frame_w = h.width;
+    ctx->frame_h = h.height;
+    ctx->frame_f64 = h.f64;
+    return RRTB_OK;
+}
+
+int rrtb_frame_attach(rrtb_ctx *ctx, rrtb_ctx *owner)
+{
+    if (!ctx || !owner || ctx == owner) return RRTB_ERR_INVALID;
+    if (!owner->d_frame) return invalid(ctx, "rrtb_frame_attach before the owner's rrtb_frame_create");
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    frame_drop_mapping(ctx);
+    if (ctx->device != owner->device) {
+        int can = 0;
+        RRTB_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, owner->device));
+        if (!can) return invalid(ctx, "no peer access between the two devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(owner->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(ctx, e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        cudaGetLastError();
+    }
+    ctx->peer_frame = owner->d_frame; // unified addressing: the owner's pointers are valid on this device
+    ctx->peer_sum = owner->d_sum;
+    ctx->peer_is_ipc = false;
+    ctx->frame_w = owner->frame_w;
+    ctx->frame_h = owner->frame_h;
+    ctx->frame_f64 = owner->frame_f64;
+    return RRTB_OK;
+}
+
+int rrtb_frame_detach(rrtb_ctx *ctx)
+{
+    if (!ctx) return RRTB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    frame_drop_mapping(ctx);
+    return RRTB_OK;
+}
+
+// enqueue: zero the own accumulator, render the shard, epilogue into the owner's frame / sum buffer
+static int enqueue_shard(rrtb_ctx *ctx, const rrtb_render_params *p)
+{
+    int rc = check_render(ctx, p);
+    if (rc) return rc;
+    void *frame = ctx->peer_frame ? ctx->peer_frame : ctx->d_frame;
+    unsigned long long *sum = ctx->peer_frame ? ctx->peer_sum : ctx->d_sum;
+    if (!frame) return invalid(ctx, "no frame: call rrtb_frame_create (owner) or rrtb_frame_import / rrtb_frame_attach first");
+    if (p->width != ctx->frame_w || p->height != ctx->frame_h) return invalid(ctx, "render size differs from the frame's");
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)3 * p->width * p->height;
+    if ((rc = reserve_accum(ctx, n))) return rc;
+    RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_accum, 0, n * sizeof(unsigned long long), ctx->stream));
+    if ((rc = launch_render(ctx, p, (uint64_t *)ctx->d_accum, nullptr, true))) return rc;
+    RRTB_CUDA(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+    if (p->shard_mode == RRTB_SHARD_TILES) rc = launch_resolve_tiles(ctx, (const uint64_t *)ctx->d_accum, frame, p, ctx->frame_f64 != 0);
+    else rc = launch_accumulate_atomic(ctx, (uint64_t *)sum, (const uint64_t *)ctx->d_accum, n);
+    if (rc) return rc;
+    RRTB_CUDA(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+    return RRTB_OK;
+}
+
+static int finish_shard(rrtb_ctx *ctx, rrtb_stats *stats)
+{
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    rrtb_stats local;
+    memset(&local, 0, sizeof(local));
+    int rc = finish_render(ctx, &local); // synchronises the stream: the peer stores of the epilogue have landed
+    if (rc) return rc;
+    float ms = 0.f;
+    RRTB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
+    local.seconds_resolve = ms * 1e-3;
+    local.kernel_launches += 1;
+    if (stats) *stats = local;
+    return RRTB_OK;
+}
+
+int rrtb_render_shard(rrtb_ctx *ctx, const rrtb_render_params *p, rrtb_stats *stats)
+{
+    if (!ctx || !p) return RRTB_ERR_INVALID;
+    int rc = enqueue_shard(ctx, p);
+    if (rc) return rc;
+    return finish_shard(ctx, stats);
+}
+
+int rrtb_frame_download(rrtb_ctx *ctx, int shard_mode, void *out_rgb)
+{
+    if (!ctx || !out_rgb) return RRTB_ERR_INVALID;
+    if (!ctx->d_frame || ctx->peer_frame) return invalid(ctx, "rrtb_frame_download is the owner's call (after rrtb_frame_create)");
+    RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)3 * ctx->frame_w * ctx->frame_h;
+    if (shard_mode == RRTB_SHARD_SAMPLES) { // the ranks added their partial sums: resolve them, then clear for the next frame
+        int rc = ctx->frame_f64 ? launch_resolve_f64(ctx, (const uint64_t *)ctx->d_sum, (double *)ctx->d_frame, n)
+                                : launch_resolve(ctx, (const uint64_t *)ctx->d_sum, (float *)ctx->d_frame, n);
+        if (rc) return rc;
+        RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_sum, 0, n * sizeof(unsigned long long), ctx->stream));
+    }
+    else if (shard_mode != RRTB_SHARD_TILES) return invalid(ctx, "bad shard_mode");
+    return copy_to_host(ctx, out_rgb, ctx->d_frame, n * (ctx->frame_f64 ? sizeof(double) : sizeof(float)));
+}
+
+int rrtb_render_group(rrtb_ctx *const *ctxs, int n, const rrtb_render_params *p, int frame_f64, void *out_rgb, rrtb_stats *stats)
+{
+    if (!ctxs || n < 1 || !p || !out_rgb) return RRTB_ERR_INVALID;
+    for (int i = 0; i < n; ++i)
+        if (!ctxs[i]) return RRTB_ERR_INVALID;
+    rrtb_ctx *owner = ctxs[0];
+    int rc;
+    if (!owner->d_frame || owner->peer_frame || owner->frame_w != p->width || owner->frame_h != p->height ||
+        owner->frame_f64 != (frame_f64 ? 1 : 0)) {
+        if ((rc = rrtb_frame_create(owner, p->width, p->height, frame_f64))) return rc;
+        for (int i = 1; i < n; ++i) frame_drop_mapping(ctxs[i]);
+    }
+    for (int i = 1; i < n; ++i)
+        if (ctxs[i]->peer_frame != owner->d_frame && (rc = rrtb_frame_attach(ctxs[i], owner))) {
+            owner->err = ctxs[i]->err;
+            return rc;
+        }
+    // every device gets its whole shard enqueued before anybody waits: the GPUs run concurrently from one host thread
+    rrtb_render_params q = *p;
+    q.world = n;
+    for (int i = 0; i < n; ++i) {
+        q.rank = i;
+        if ((rc = enqueue_shard(ctxs[i], &q))) {
+            owner->err = ctxs[i]->err;
+            return rc;
+        }
+    }
+    rrtb_stats total;
+    memset(&total, 0, sizeof(total));
+    for (int i = 0; i < n; ++i) {
+        rrtb_stats st;
+        if ((rc = finish_shard(ctxs[i], &st))) {
+            owner->err = ctxs[i]->err;
+            return rc;
+        }
+        total.seconds_render = st.seconds_render > total.seconds_render ? st.seconds_render : total.seconds_render;
+        total.seconds_resolve = st.seconds_resolve > total.seconds_resolve ? st.seconds_resolve : total.seconds_resolve;
+        total.seconds_build = st.seconds_build > total.seconds_build ? st.seconds_build : total.seconds_build;
+        total.rays += st.rays; total.paths += st.paths; total.box_tests += st.box_tests; total.sphere_tests += st.sphere_tests;
+        total.msphere_tests += st.msphere_tests; total.triangle_tests += st.triangle_tests; total.hits += st.hits;
+        total.kernel_launches += st.kernel_launches;
+    }
+    if ((rc = rrtb_frame_download(owner, p->shard_mode, out_rgb))) return rc;
+    if (stats) *stats = total;
+    return RRTB_OK;
+}
+
+void *rrtb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void rrtb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 int rrtb_probe_issue_rate(rrtb_ctx *ctx, double *ffma_lane_instr_per_s, double *mix_lane_instr_per_s)

@@ -13,7 +13,7 @@
 struct rrtb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_copy[2] = {nullptr, nullptr};
     int sm_count = 0;
     std::string err;
 
@@ -54,6 +54,19 @@ struct rrtb_ctx {
     float *d_rgb = nullptr;                   // host-path float framebuffer
     size_t accum_elems = 0;
     unsigned char *d_stage = nullptr;         // raw scene structs of the last upload (input of k_prepare)
+    rrtb_render_params pending{};             // the render enqueued by launch_render, for finish_render
+    int pending_launches = 0;
+    // multi-GPU frame: the owner (rank 0) holds the float/double frame every rank's resolve epilogue stores its
+    // tiles into, and the 64-bit sum buffer sample shards add into; other ranks hold peer mappings of both
+    void *d_frame = nullptr;                  // owner: 3*W*H doubles' worth of room (float or double frame)
+    unsigned long long *d_sum = nullptr;      // owner: 3*W*H fixed-point sums of a sample-sharded frame
+    size_t frame_elems = 0;                   // 3*W*H the frame was sized for
+    int frame_w = 0, frame_h = 0, frame_f64 = 0;
+    void *peer_frame = nullptr;               // non-owner: the owner's d_frame / d_sum (IPC mapping or same-process pointer)
+    unsigned long long *peer_sum = nullptr;
+    bool peer_is_ipc = false;
+    void *h_pinned = nullptr;                 // pinned staging for device->host copies into pageable user buffers
+    size_t h_pinned_bytes = 0;
     // Device buffers are grow-only: rrtb_scene_set re-uses them when the next scene fits (a frame loop that re-sends
     // its scene pays no cudaMalloc / cudaFree).  Capacity in bytes, keyed by the address of the pointer member.
     std::unordered_map<const void *, size_t> capacity;
@@ -76,7 +89,10 @@ void free_scene(rrtb_ctx *ctx);
 // rrtb_render.cu
 DeviceScene device_scene(const rrtb_ctx *ctx);
 DeviceCamera device_camera(const rrtb_camera &c, int W, int H);
-int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum, rrtb_stats *stats);
+int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum, rrtb_stats *stats, bool defer = false);
+int finish_render(rrtb_ctx *ctx, rrtb_stats *stats);
+int launch_resolve_tiles(rrtb_ctx *ctx, const uint64_t *d_accum, void *d_out, const rrtb_render_params *p, bool f64);
+int launch_accumulate_atomic(rrtb_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t n);
 int launch_resolve(rrtb_ctx *ctx, const uint64_t *d_accum, float *d_out, size_t n);
 int launch_resolve_f64(rrtb_ctx *ctx, const uint64_t *d_accum, double *d_out, size_t n);
 int launch_accumulate(rrtb_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t n);

@@ -197,6 +197,40 @@ __global__ void k_resolve_f64(const unsigned long long *__restrict__ acc, double
     for (; i < n; i += stride) out[i] = (double)acc[i] * 9.094947017729282e-13; // exact for sums below 2^53
 }
 
+// Multi-GPU epilogue of a tile shard: one warp per OWNED 8x4-pixel tile converts its 32 accumulators and
+// stores them as 3 floats (or doubles) straight into the owner's frame -- `out` is rank 0's buffer, for ranks > 0 a
+// peer mapping over NVLink.  Tiles are disjoint, so the frame needs neither a zero-fill nor a reduction:
+// 12 B/pixel/GPU cross the link instead of a 24 B/pixel full-frame integer reduce.
+template <typename T>
+__global__ void __launch_bounds__(256) k_resolve_tiles(const unsigned long long *__restrict__ acc, T *out, int W, int H,
+                                                        int tiles_x, int n_tiles, int rank, int world)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int tile = rank + warp * world; tile < n_tiles; tile += n_warps * world) {
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int i = tx * 8 + (lane & 7), j = ty * 4 + (lane >> 3);
+        if (i < W && j < H) {
+            const size_t k = 3 * ((size_t)j * W + i);
+            out[k + 0] = (T)((double)acc[k + 0] * 9.094947017729282e-13); // 2^-40; float: one rounding, as k_resolve
+            out[k + 1] = (T)((double)acc[k + 1] * 9.094947017729282e-13);
+            out[k + 2] = (T)((double)acc[k + 2] * 9.094947017729282e-13);
+        }
+    }
+}
+
+// Multi-GPU epilogue of a sample shard: the partial sums are ADDED into the owner's 64-bit accumulator (integer
+// atomics, over NVLink for ranks > 0): associative, so the image does not depend on the arrival order.
+__global__ void k_accumulate_atomic(unsigned long long *dst, const unsigned long long *__restrict__ src, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const unsigned long long v = src[i];
+        if (v) atomicAdd(dst + i, v);
+    }
+}
+
 __global__ void k_accumulate(unsigned long long *__restrict__ dst, const unsigned long long *__restrict__ src, size_t n)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -399,7 +433,7 @@ static int launch_render_t(rrtb_ctx *ctx, const RenderArgs &args, int *blocks_ou
     return launch_persistent(ctx, k_render<B, C>, args, blocks_out);
 }
 
-int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum, rrtb_stats *stats)
+int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum, rrtb_stats *stats, bool defer)
 {
     RenderArgs a;
     a.scene = device_scene(ctx);
@@ -486,6 +520,17 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     }
     RRTB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     RRTB_CUDA(ctx, cudaGetLastError());
+    ctx->pending = *p;
+    ctx->pending_launches = launches;
+    if (defer) return RRTB_OK; // the caller enqueues more work (other devices, the resolve) before finish_render
+    return finish_render(ctx, stats);
+}
+
+// Waits for the render enqueued by launch_render and fills `stats` (device time by CUDA events on the context stream,
+// counters of the counting build, camera paths of the shard).
+int finish_render(rrtb_ctx *ctx, rrtb_stats *stats)
+{
+    const rrtb_render_params *p = &ctx->pending;
     RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     RRTB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -493,7 +538,7 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
         stats->seconds_render = ms * 1e-3;
         stats->seconds_build = ctx->seconds_build;
         stats->seconds_resolve = 0.0;
-        stats->kernel_launches = launches;
+        stats->kernel_launches = ctx->pending_launches;
         stats->rays = stats->box_tests = stats->sphere_tests = stats->msphere_tests = stats->triangle_tests = stats->hits = 0;
         if (p->count_rays) {
             unsigned long long c[8];
@@ -506,18 +551,22 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
             stats->hits = c[6];
         }
         // camera paths in this shard
+        const int world = p->world < 1 ? 1 : p->world, rank = p->world < 1 ? 0 : p->rank;
+        const int tiles_x = (p->width + 7) / 8, tiles_y = (p->height + 3) / 4, n_tiles = tiles_x * tiles_y;
         unsigned long long px = 0;
-        if (a.shard_mode == RRTB_SHARD_TILES && a.world > 1) {
-            for (int t = a.rank; t < n_tiles; t += a.world) {
-                int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
-                int w = min(8, a.W - tx * 8), h = min(4, a.H - ty * 4);
+        int n_local_samples = p->spp;
+        if (p->shard_mode == RRTB_SHARD_TILES && world > 1) {
+            for (int t = rank; t < n_tiles; t += world) {
+                int ty = t / tiles_x, tx = t - ty * tiles_x;
+                int w = min(8, p->width - tx * 8), h = min(4, p->height - ty * 4);
                 px += (unsigned long long)(w * h);
             }
         }
         else {
-            px = (unsigned long long)a.W * a.H;
+            px = (unsigned long long)p->width * p->height;
+            if (p->shard_mode == RRTB_SHARD_SAMPLES) n_local_samples = max((p->spp - rank + world - 1) / world, 0);
         }
-        stats->paths = px * (unsigned long long)a.n_local_samples;
+        stats->paths = px * (unsigned long long)n_local_samples;
 #ifdef RRTB_DEBUG_CHECKS
         unsigned int viol = 0;
         RRTB_CUDA(ctx, cudaMemcpyFromSymbol(&viol, g_rrtb_violations, sizeof(viol)));
@@ -543,6 +592,34 @@ int launch_resolve_f64(rrtb_ctx *ctx, const uint64_t *d_accum, double *d_out, si
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
     if (blocks < 1) blocks = 1;
     k_resolve_f64<<<blocks, 256, 0, ctx->stream>>>((const unsigned long long *)d_accum, d_out, n);
+    RRTB_CUDA(ctx, cudaGetLastError());
+    return RRTB_OK;
+}
+
+int launch_resolve_tiles(rrtb_ctx *ctx, const uint64_t *d_accum, void *d_out, const rrtb_render_params *p, bool f64)
+{
+    const int tiles_x = (p->width + 7) / 8, tiles_y = (p->height + 3) / 4, n_tiles = tiles_x * tiles_y;
+    const int world = p->world < 1 ? 1 : p->world, rank = p->world < 1 ? 0 : p->rank;
+    const int own = (n_tiles - rank + world - 1) / world;
+    int blocks = (own + 7) / 8; // 8 warps per block, one tile per warp and trip
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    if (f64)
+        k_resolve_tiles<double><<<blocks, 256, 0, ctx->stream>>>((const unsigned long long *)d_accum, (double *)d_out, p->width, p->height,
+                                                                 tiles_x, n_tiles, rank, world);
+    else
+        k_resolve_tiles<float><<<blocks, 256, 0, ctx->stream>>>((const unsigned long long *)d_accum, (float *)d_out, p->width, p->height,
+                                                                tiles_x, n_tiles, rank, world);
+    RRTB_CUDA(ctx, cudaGetLastError());
+    return RRTB_OK;
+}
+
+int launch_accumulate_atomic(rrtb_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, size_t n)
+{
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    k_accumulate_atomic<<<blocks, 256, 0, ctx->stream>>>((unsigned long long *)d_dst, (const unsigned long long *)d_src, n);
     RRTB_CUDA(ctx, cudaGetLastError());
     return RRTB_OK;
 }

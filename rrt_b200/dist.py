@@ -2,16 +2,17 @@
 
 The reference has no multi-GPU path at all (`-D <n>` selects ONE device, main.cpp:107-110).
 The path shards trivially -- pixels and samples are independent -- so there is no data-path collective
-inside the render: every rank renders its shard of the SAME image into a full-size 64-bit fixed-point
-accumulator (zero where it owns nothing) and the only exchange is ONE sum of those accumulators onto
-rank 0.  Integer addition is associative, so the reduced image is bit-identical to the single-GPU image
-for any world size, either shard mode and any reduction order.
+inside the render.  The combine is done by the library's own kernels over NVLink peer memory
+(include/rrtb.h "multi-GPU"): rank 0 owns the frame, the other ranks map it once (CUDA IPC handle sent with one
+`broadcast_object_list`), and every rank's resolve epilogue writes its shard straight into it:
 
-  RRTB_SHARD_TILES    interleaved 8x4-pixel tiles, tile t -> rank t % world  (default)
-  RRTB_SHARD_SAMPLES  sample s -> rank s % world   (very high spp on small images)
+  RRTB_SHARD_TILES    interleaved 8x4-pixel tiles, tile t -> rank t % world  (default): the tiles are
+                      disjoint, each rank STORES its own as float3 -- 12 B/pixel/world over the link, no reduce
+  RRTB_SHARD_SAMPLES  sample s -> rank s % world   (very high spp on small images): 64-bit fixed-point
+                      partial sums ADDED with integer atomics; associative, so bit-identical for any order
 
-The reduce is NCCL over NVLink/NVSwitch (`reduce_accumulators`); the message is 24 B/pixel (23 MB at
-1200x800, 199 MB at 4K) against seconds of rendering.
+torch.distributed only carries the handle and the two barriers per frame.  `reduce_accumulators` (an NCCL / gloo
+sum of full-size accumulators) remains for callers that keep their shards in torch tensors, and for the CPU tests.
 """
 import os
 
@@ -61,7 +62,7 @@ def reduce_accumulators(acc, dst=0, group=None):
 
 
 class DistributedRenderer:
-    """One instance per rank.  render() returns the float32 [H, W, 3] sums on rank 0 (None elsewhere)."""
+    """One instance per rank.  render() returns the [H, W, 3] sums on rank 0 (None elsewhere)."""
 
     def __init__(self, ctx, rank=None, world=None, group=None):
         r, w, _ = env_rank_world()
@@ -69,23 +70,40 @@ class DistributedRenderer:
         self.rank = r if rank is None else rank
         self.world = w if world is None else world
         self.group = group
+        self._frame = None  # (width, height, f64) the mapping was made for
 
-    def render(self, width, height, spp, max_depth=50, seed=1984, shard_mode=None, to_host=True):
-        import torch
+    def _barrier(self):
+        import torch.distributed as dist
 
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def ensure_frame(self, width, height, f64=False):
+        """Rank 0 creates (or re-uses) the frame, the others map it.  Collective."""
+        import torch.distributed as dist
+
+        if self._frame == (width, height, f64):
+            return
+        box = [None]
+        if self.rank == 0:
+            self.ctx.frame_create(width, height, f64)
+            box[0] = self.ctx.frame_export()
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=0, group=self.group)
+            if self.rank != 0:
+                self.ctx.frame_import(box[0])
+        self._frame = (width, height, f64)
+
+    def render(self, width, height, spp, max_depth=50, seed=1984, shard_mode=None, out=None, precision="f32", dtype=np.float32):
         mode = choose_shard_mode(width, height, spp, self.world) if shard_mode is None else shard_mode
-        dev = torch.device("cuda", self.ctx.device)
-        n = 3 * width * height
-        acc = torch.zeros(n, dtype=torch.int64, device=dev)
-        torch.cuda.synchronize(dev)
-        p = self.ctx.params(width, height, spp, max_depth, seed, self.rank, self.world, mode)
-        stats = self.ctx.render_device(p, acc.data_ptr())
-        reduce_accumulators(acc, 0, self.group)
-        torch.cuda.synchronize(dev)
+        f64 = np.dtype(dtype) == np.dtype(np.float64)
+        self.ensure_frame(width, height, f64)
+        p = self.ctx.params(width, height, spp, max_depth, seed, self.rank, self.world, mode, precision=precision)
+        self._barrier()  # the previous frame has been downloaded
+        stats = self.ctx.render_shard(p)
+        self._barrier()  # every rank's stores have landed in the owner's frame
         if self.rank != 0:
             return None, stats
-        out = torch.empty(n, dtype=torch.float32, device=dev)
-        self.ctx.resolve_device(acc.data_ptr(), out.data_ptr(), n)
-        if to_host:
-            return out.cpu().numpy().reshape(height, width, 3), stats
-        return out.view(height, width, 3), stats
+        if out is None:
+            out = np.empty((height, width, 3), dtype)
+        return self.ctx.frame_download(out, mode), stats

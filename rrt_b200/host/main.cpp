@@ -3,6 +3,7 @@
 // Same command line, same stdout/stderr protocol and same exit codes as the reference's main.cpp:
 //   flags            -i -o -w -h -s -d -b -tx -ty -q -D          (reference main.cpp:69-119; -h is HEIGHT)
 //   additions        -S <seed>  (Philox key, default 1984 = the reference's curand seed, rrt.cu:88)
+//                    -R         count ray segments in a second, untimed pass (Mrays/s in the stats line; off: 0)
 //                    -I <list>  frame batch (reference README.md:64 to-do "input list of scenes to render")
 //                    -G <n>     n GPUs of this box: one context + one host thread per GPU, each renders its
 //                               interleaved tiles; the shards are disjoint, so summing them is exact
@@ -21,7 +22,6 @@
 #include <fstream>
 #include <iostream>
 #include <memory>
-#include <thread>
 #include <vector>
 #include <string>
 #include <unistd.h>
@@ -61,6 +61,7 @@ static void usage(const char *argv)
     std::cerr << "  -q                  : query devices & cuda info\n";
     std::cerr << "  -D <device number>  : use this cuda device (0)\n";
     std::cerr << "  -S <seed>           : random seed (1984)\n";
+    std::cerr << "  -R                  : count ray segments in a second untimed pass (rays, Mrays/s in the stats line)\n";
     std::cerr << "  -G <n>              : render on n GPUs (devices D..D+n-1), interleaved 8x4-pixel tiles (1)\n";
     std::cerr << "  -I list.txt         : frame batch: one '<scene.txt> <out.png>' per line; scenes that differ only\n";
     std::cerr << "                        in their camera reuse the uploaded scene and its BVH\n";
@@ -113,7 +114,7 @@ static rrtb_scene *load_scene_or_exit(const std::string &filename, int w, int h,
 
 // -I list: "<scene.txt> <out.png>" per line, one context, geometry uploaded only when it changes
 static int run_batch(const std::string &list, int w, int h, int spp, int depth, bool use_bvh, int tx, int ty, int device,
-                     unsigned long long seed)
+                     unsigned long long seed, bool count_rays)
 {
     std::ifstream fl(list);
     if (!fl.good()) {
@@ -121,6 +122,7 @@ static int run_batch(const std::string &list, int w, int h, int spp, int depth, 
         return 2;
     }
     Rrt rrt(w, h, spp, depth, use_bvh, tx, ty, device, seed);
+    rrt.count_rays = count_rays;
     rrtb_scene *prev = nullptr;
     std::string scene_file, png_file;
     std::vector<uint8_t> rgb((size_t)w * h * 3);
@@ -166,6 +168,7 @@ int main(int argc, char *argv[])
     unsigned long long seed = 1984;
     std::string batch_list;
     int n_gpus = 1;
+    bool count_rays = false;
 
     // Only the first letter after '-' is examined, as in the reference (so "-input" == "-i").
     for (int i = 1; i < argc; ++i) {
@@ -192,12 +195,13 @@ int main(int argc, char *argv[])
         else if (c == 'S') seed = strtoull(next(), nullptr, 10);
         else if (c == 'I') batch_list = next();
         else if (c == 'G') n_gpus = atoi(next());
+        else if (c == 'R') count_rays = true;
         else usage(argv[i]);
     }
 
     if (batch_list != "")
         return run_batch(batch_list, image_width, image_height, num_samples, max_depth, use_bvh, num_threads_x, num_threads_y,
-                         device, seed);
+                         device, seed, count_rays);
 
     rrtb_scene *the_scene = nullptr;
     if (the_scene_filename != "") {
@@ -227,13 +231,16 @@ int main(int argc, char *argv[])
     std::time_t render_time = std::time(nullptr);
     std::tm render_tm = *std::localtime(&render_time);
 
-    // rank 0 renders in this thread; -G n adds n-1 more contexts, one host thread each
-    Rrt rrt(image_width, image_height, num_samples, max_depth, use_bvh, num_threads_x, num_threads_y, device, seed, 0,
-            n_gpus < 1 ? 1 : n_gpus);
+    // -G n: n contexts, one per device D..D+n-1 (RRTB_GROUP_SAME_DEVICE=1: all on device D, a test aid for boxes with
+    // one GPU); ONE library call renders all shards and combines them over NVLink (rrtb_render_group)
+    if (n_gpus < 1) n_gpus = 1;
+    const bool same_device = getenv("RRTB_GROUP_SAME_DEVICE") != nullptr;
+    Rrt rrt(image_width, image_height, num_samples, max_depth, use_bvh, num_threads_x, num_threads_y, device, seed);
+    rrt.count_rays = count_rays;
     std::vector<std::unique_ptr<Rrt>> peers;
     for (int r = 1; r < n_gpus; ++r)
         peers.emplace_back(new Rrt(image_width, image_height, num_samples, max_depth, use_bvh, num_threads_x, num_threads_y,
-                                   device + r, seed, r, n_gpus));
+                                   same_device ? device : device + r, seed));
     std::cerr << "Rendering a " << image_width << "x" << image_height << " image with " << num_samples
               << " samples per pixel on a persistent sm_100a kernel.\n";
     int32_t c[6];
@@ -241,18 +248,14 @@ int main(int argc, char *argv[])
     std::cerr << "num_hittables = " << (c[1] + c[2] + c[3]) << "\n";
     std::cerr << "CUDA Device: " << device << std::endl;
 
-    std::vector<vec3 *> peer_fb(peers.size(), nullptr);
-    std::vector<std::thread> workers;
-    for (size_t r = 0; r < peers.size(); ++r)
-        workers.emplace_back([&, r]() { peer_fb[r] = peers[r]->render(the_scene); });
-    vec3 *fb = rrt.render(the_scene);
-    for (auto &w : workers) w.join();
-    for (size_t r = 0; r < peers.size(); ++r) { // shards are disjoint (zeros elsewhere): the sum is exact
-        const size_t n = (size_t)image_width * image_height;
-        for (size_t k = 0; k < n; ++k)
-            for (int ch = 0; ch < 3; ++ch) fb[k].e[ch] += peer_fb[r][k].e[ch];
-        rrt.stats.rays += peers[r]->stats.rays;
-        rrt.stats.seconds_render = std::max(rrt.stats.seconds_render, peers[r]->stats.seconds_render);
+    vec3 *fb;
+    if (n_gpus == 1) {
+        fb = rrt.render(the_scene);
+    }
+    else {
+        std::vector<Rrt *> others;
+        for (auto &q : peers) others.push_back(q.get());
+        fb = rrt.render_group(the_scene, others);
     }
 
     const double timer_seconds = rrt.stats.seconds_render;

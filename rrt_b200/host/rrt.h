@@ -87,9 +87,45 @@ class Rrt {
         p.rank = rank;
         p.world = world;
         p.shard_mode = RRTB_SHARD_TILES;
-        p.count_rays = 1;
+        p.count_rays = 0; // the timed render is the kernel without counters (what bench.py measures)
         p.precision = RRTB_FP_PRECISION;
         rrtb_check(rrtb_render_fp(ctx, &p, &fb[0].e[0], &stats), ctx, "rrtb_render");
+        if (count_rays) { // -R: a second, untimed pass of the counting build fills stats.rays and the per-ray work counters
+            std::vector<vec3> scratch(fb.size());
+            rrtb_stats counted;
+            p.count_rays = 1;
+            rrtb_check(rrtb_render_fp(ctx, &p, &scratch[0].e[0], &counted), ctx, "rrtb_render (counting pass)");
+            stats.rays = counted.rays;
+            stats.hits = counted.hits;
+            stats.box_tests = counted.box_tests;
+            stats.sphere_tests = counted.sphere_tests;
+            stats.msphere_tests = counted.msphere_tests;
+            stats.triangle_tests = counted.triangle_tests;
+        }
+        return fb.data();
+    }
+
+    bool count_rays = false;
+
+    // -G n: this object owns the frame; `peers` (same image parameters, other devices, scene not yet loaded) render
+    // the other shards.  One call into the library drives all devices (rrtb_render_group): every GPU's epilogue
+    // stores its tiles into this object's frame over NVLink.
+    vec3 *render_group(const rrtb_scene *the_scene, const std::vector<Rrt *> &peers)
+    {
+        std::vector<rrtb_ctx *> ctxs(1, ctx);
+        for (Rrt *r : peers) ctxs.push_back(r->ctx);
+        for (rrtb_ctx *c : ctxs) rrtb_check(rrtb_scene_upload(c, the_scene, bvh ? 1 : 0), c, "rrtb_scene_upload");
+        fb.resize((size_t)image_width * image_height);
+        rrtb_render_params p{};
+        p.width = image_width;
+        p.height = image_height;
+        p.spp = samples_per_pixel;
+        p.max_depth = max_depth;
+        p.seed = seed;
+        p.shard_mode = RRTB_SHARD_TILES;
+        p.count_rays = count_rays ? 1 : 0;
+        p.precision = RRTB_FP_PRECISION;
+        rrtb_check(rrtb_render_group(ctxs.data(), (int)ctxs.size(), &p, sizeof(FP_T) == 8, &fb[0].e[0], &stats), ctx, "rrtb_render_group");
         return fb.data();
     }
 

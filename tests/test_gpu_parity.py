@@ -256,19 +256,21 @@ def test_cli_drop_in(tmp_path, built_lib):
 
 
 @pytest.mark.slow
-def test_psnr_vs_rrtd_full_size_live(ctx, tmp_path):
-    """The north-star bar verbatim: PSNR >= 40 dB against the reference `rrtd` (rrt.cu, double, rebuilt for
-    sm_100a by oracle/Makefile) render of scenes/final.txt at 1200x800, 500 spp, executed on this very box."""
+@pytest.mark.parametrize("name,W,H,spp", [("final", 1200, 800, 500), ("test2", 1920, 1080, 256), ("test3", 1920, 1080, 256)])
+def test_psnr_vs_rrtd_full_size_live(ctx, tmp_path, name, W, H, spp):
+    """The north-star bar verbatim, at the sizes of BASELINE.json configs[1..3]: PSNR >= 40 dB against the reference
+    `rrtd` (rrt.cu, double, rebuilt for sm_100a by oracle/Makefile) render of the same scene at the same size and spp,
+    executed on this very box: scenes/final.txt 1200x800 / 500 spp, the triangle scene and the motion-blur scene at
+    1920x1080 / 256 spp."""
     from PIL import Image
 
     from oracle_lib import REF_DIR, ref_scene_path
     from rrt_b200 import Scene, tonemap
 
     exe = os.path.join(REF_DIR, "rrtd")
-    scene_path = ref_scene_path("final.txt")
+    scene_path = ref_scene_path(name + ".txt")
     if not (os.path.exists(exe) and scene_path):
         pytest.skip("oracle/_ref/rrtd or the scene text is not staged")
-    W, H, spp = 1200, 800, 500
     out = tmp_path / "rrtd.png"
     r = subprocess.run([exe, "-i", scene_path, "-w", str(W), "-h", str(H), "-s", str(spp), "-d", "50", "-o", str(out)],
                        capture_output=True, text=True, timeout=900)
@@ -278,5 +280,6 @@ def test_psnr_vs_rrtd_full_size_live(ctx, tmp_path):
     img, st = ctx.render(W, H, spp, 50, seed=1984)
     ours = tonemap(img, spp)
     val = psnr(ours, ref)
-    print("PSNR vs rrtd (final.txt 1200x800 500 spp): %.2f dB; rrtd stats: %s" % (val, [l for l in r.stderr.splitlines() if l.startswith("stats,")]))
-    assert val >= 40.0, val
+    print("PSNR vs rrtd (%s.txt %dx%d %d spp): %.2f dB; rrtd stats: %s" % (name, W, H, spp, val, [l for l in r.stderr.splitlines() if l.startswith("stats,")]))
+    assert val >= 40.0, (name, val)
+    assert abs(ours.astype(np.float64).mean() - ref.astype(np.float64).mean()) < 0.5
