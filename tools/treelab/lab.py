@@ -89,7 +89,7 @@ def run(scene, rays, label=""):
     trees = {}
     trees["lbvh"] = C.c_void_p(L.lab_from_arrays(n, vp(pbox), vp(ba["left"]), vp(ba["right"]), vp(ba["perm"])))
     trees["sah"] = C.c_void_p(L.lab_build_sah(n, vp(pbox)))
-    for r in (8, 16, 100):
+    for r in ():
         trees["ploc%d" % r] = C.c_void_p(L.lab_build_ploc(n, vp(pbox), vp(ba["perm"]), r))
     for name, t in trees.items():
         c = LabCounters()
@@ -101,7 +101,8 @@ def run(scene, rays, label=""):
             for q in (0,):
                 w = C.c_void_p(L.lab_collapse(t, k))
                 L.lab_quantise(w, q)
-                for cull, om in ((0, 1),):
+                L.lab_axis_sort(w)
+                for cull, om in ((0, 0), (0, 1), (0, 2)):
                     L.lab_set_order(om)
                     c = LabCounters()
                     L.lab_trace_wide(w, C.byref(o._s), vp(rays), m, C.c_float(0.001), cull, C.byref(c), vp(ids))

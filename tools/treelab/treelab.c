@@ -96,7 +96,7 @@ void lab_trace_binary(const btree *t,const orc_scene *s,const float *rays7,int m
 }
 
 /* ---- wide tree collapsed from a binary tree ---- */
-typedef struct { int k; int n_nodes; int *child; /* [n_nodes*k] >=0 node, <0 leaf ~prim, INT32_MAX empty */ box_t *cbox; } wtree;
+typedef struct { int k; int n_nodes; int *axis; int *child; /* [n_nodes*k] >=0 node, <0 leaf ~prim, INT32_MAX empty */ box_t *cbox; } wtree;
 #define W_EMPTY 0x7fffffff
 static int collapse_rec(const btree *t,wtree *w,int bnode){
   int me=w->n_nodes++; int k=w->k; int ch[16]; int nc=0; ch[nc++]=t->left[bnode]; ch[nc++]=t->right[bnode];
@@ -105,7 +105,13 @@ static int collapse_rec(const btree *t,wtree *w,int bnode){
   for(int i=0;i<nc;i++){ w->child[me*k+i]= ch[i]>=0? collapse_rec(t,w,ch[i]) : ch[i]; }
   return me;
 }
-wtree *lab_collapse(const btree *t,int k){ wtree *w=calloc(1,sizeof(wtree)); w->k=k; w->child=malloc(sizeof(int)*t->n*k); w->cbox=malloc(sizeof(box_t)*t->n*k); w->n_nodes=0; if(t->n>1)collapse_rec(t,w,t->root); return w; }
+wtree *lab_collapse(const btree *t,int k){ wtree *w=calloc(1,sizeof(wtree)); w->k=k; w->child=malloc(sizeof(int)*t->n*k); w->cbox=malloc(sizeof(box_t)*t->n*k); w->n_nodes=0; if(t->n>1)collapse_rec(t,w,t->root); w->axis=NULL; return w; }
+/* sort each node's children ascending along the axis with the largest spread of child-box centres (empties last) */
+void lab_axis_sort(wtree *w){ int k=w->k; w->axis=malloc(sizeof(int)*w->n_nodes);
+  for(int n=0;n<w->n_nodes;n++){ float lo[3]={INFINITY,INFINITY,INFINITY},hi[3]={-INFINITY,-INFINITY,-INFINITY}; int nc=0;
+    for(int i=0;i<k;i++) if(w->child[n*k+i]!=W_EMPTY){nc++; for(int a=0;a<3;a++){float c=w->cbox[n*k+i].lo[a]+w->cbox[n*k+i].hi[a]; if(c<lo[a])lo[a]=c; if(c>hi[a])hi[a]=c;}}
+    int ax=0; for(int a=1;a<3;a++) if(hi[a]-lo[a]>hi[ax]-lo[ax]) ax=a; w->axis[n]=ax;
+    for(int i=1;i<k;i++){ int c=w->child[n*k+i]; box_t b=w->cbox[n*k+i]; if(c==W_EMPTY)continue; float key=b.lo[ax]+b.hi[ax]; int j=i; while(j>0 && (w->child[n*k+j-1]==W_EMPTY || w->cbox[n*k+j-1].lo[ax]+w->cbox[n*k+j-1].hi[ax]>key)){ w->child[n*k+j]=w->child[n*k+j-1]; w->cbox[n*k+j]=w->cbox[n*k+j-1]; j--; } w->child[n*k+j]=c; w->cbox[n*k+j]=b; } } }
 int lab_wide_nodes(const wtree *w){return w->n_nodes;}
 double lab_wide_fill(const wtree *w){ uint64_t c=0; for(int i=0;i<w->n_nodes*w->k;i++) if(w->child[i]!=W_EMPTY)c++; return (double)c/(w->n_nodes*w->k); }
 
@@ -124,6 +130,9 @@ void lab_trace_wide(const wtree *w,const orc_scene *s,const float *rays7,int m,f
       if(cur>=0){ c->visits++; int hc[16]; float ht[16]; int nh=0;
         for(int j=0;j<k;j++){ int ch=w->child[cur*k+j]; if(ch==W_EMPTY)continue; c->box_tests++; float te; if(slab(&w->cbox[cur*k+j],&r,tmin,best,&te)){ int p=nh++; while(p>0&&ht[p-1]>te){hc[p]=hc[p-1];ht[p]=ht[p-1];p--;} hc[p]=ch;ht[p]=te; } }
         if(nh>2&&g_order_mode==1){ /* nearest first, the rest in slot order */ int n0=hc[0]; float t0=ht[0]; int q=0; int hc2[16]; float ht2[16]; hc2[q]=n0;ht2[q]=t0;q++; for(int j=0;j<k;j++){int ch=w->child[cur*k+j]; if(ch==W_EMPTY||ch==n0)continue; for(int z=1;z<nh;z++) if(hc[z]==ch){hc2[q]=ch;ht2[q]=ht[z];q++;}} for(int z=0;z<nh;z++){hc[z]=hc2[z];ht[z]=ht2[z];} }
+        if(g_order_mode==2&&w->axis){ int rev=r.d[w->axis[cur]]<0; int q=0; int hc2[16]; float ht2[16];
+          for(int jj=0;jj<k;jj++){ int j=rev?k-1-jj:jj; int ch=w->child[cur*k+j]; if(ch==W_EMPTY)continue; for(int z=0;z<nh;z++) if(hc[z]==ch){hc2[q]=ch;ht2[q]=ht[z];q++;} }
+          for(int z=0;z<nh;z++){hc[z]=hc2[z];ht[z]=ht2[z];} }
         if(nh==0){cur=INT32_MIN;} else { for(int j=nh-1;j>=1;j--){stack[sp]=hc[j];stt[sp]=ht[j];sp++;c->pushes++;} if((uint64_t)sp>c->maxstack)c->maxstack=sp; cur=hc[0]; }
       } else { leaf_hit(s,~cur,r7,tmin,&best,&bid,c); cur=INT32_MIN; }
       if(cur==INT32_MIN){ while(sp){ --sp; if(cull_pop==1&&stt[sp]>best)continue; if(cull_pop==2&&stack[sp]<0&&stt[sp]>best)continue; cur=stack[sp]; break; } }
