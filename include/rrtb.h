@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RRTB_ABI_VERSION 2
+#define RRTB_ABI_VERSION 3
 
 typedef enum rrtb_status {
     RRTB_OK = 0,
@@ -79,17 +79,24 @@ typedef struct rrtb_triangle { /* world-space, already instanced (scene.h:157-17
 } rrtb_triangle;
 
 /* SURVEY 8f4 -- "motion blur for object instances" (the reference's README.md:62 to-do; it has no such
- * primitive, the model below follows its moving_sphere.h:27-30): a triangle of an instance that TRANSLATES
- * linearly by `delta` between time0 and time1.  Vertices are given at time0.  The library works on
- *   rate[k] = delta[k] / (time1 - time0),  base[k] = fma(-rate[k], time0, v0[k])      (float)
- *   v0(time) = fma(rate, time, base);  v1(time) = v0(time) + (v1 - v0);  v2(time) = v0(time) + (v2 - v0)
- * Its box spans the camera's shutter interval, as a moving sphere's does (rrt.cu:169).  Object ids of moving
- * triangles follow the static triangles'. */
+ * primitive, the model below follows its moving_sphere.h:27-30): a triangle of an instance whose pose changes
+ * between time0 and time1.  Vertices are given at time0; until time1 vertex 0 moves by `delta`, vertex 1 by
+ * delta + extra1 and vertex 2 by delta + extra2, each linearly in time -- the keyframe interpolation renderers use
+ * for transformation motion blur.  extra1 = extra2 = 0 is a pure translation (scene line `mobj`); an instance that
+ * rotates or scales between two poses (scene line `kobj`) has non-zero extras.  The library works on
+ *   rate[k]  = delta[k] / (time1 - time0)              base[k]  = fma(-rate[k],  time0, v0[k])            (float)
+ *   rate1[k] = extra1[k] / (time1 - time0)             base1[k] = fma(-rate1[k], time0, v1[k] - v0[k])
+ *   rate2[k] = extra2[k] / (time1 - time0)             base2[k] = fma(-rate2[k], time0, v2[k] - v0[k])
+ *   v0(t) = fma(rate, t, base);  e1(t) = fma(rate1, t, base1);  e2(t) = fma(rate2, t, base2);  v1 = v0 + e1, v2 = v0 + e2
+ * (a zero rate keeps its base exactly).  The box spans the camera's shutter interval, as a moving sphere's does
+ * (rrt.cu:169): motion is linear, so the two end poses bound every pose in between.  The face normal is that of the
+ * pose at the ray's time.  Object ids of moving triangles follow the static triangles'. */
 typedef struct rrtb_mtriangle {
     float v0[3], v1[3], v2[3];
     float delta[3];
     float time0, time1;
     int32_t material;
+    float extra1[3], extra2[3];
 } rrtb_mtriangle;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -121,7 +128,10 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
 /* Stage moving triangles for the NEXT rrtb_scene_set / rrtb_scene_upload on this context, which
  * consumes them (a later rrtb_scene_set without a new staging call has none).  n == 0 clears the stage. */
 int rrtb_scene_stage_moving_triangles(rrtb_ctx *ctx, const rrtb_mtriangle *mtriangles, int n_mtriangles);
-/* Replace only the camera (animation frames that differ in the camera only). */
+/* Replace only the camera (animation frames that differ in the camera only).  The primitives stay on the
+ * device.  If the scene has moving primitives and the shutter interval changed (their boxes span it, rrt.cu:169), or
+ * the camera moved farther from the origin than the one the traversal boxes were padded for, the LBVH is rebuilt on
+ * the device from the retained scene (stats.seconds_build reports it); otherwise nothing is rebuilt. */
 int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam);
 
 /* ---- render ------------------------------------------------------------------------------------
@@ -274,10 +284,13 @@ int rrtb_scatter_f64(rrtb_ctx *ctx, const double *in16, const uint32_t *rnd4, in
 
 typedef struct rrtb_scene rrtb_scene;
 
-/* One grammar EXTENSION (a line the reference ignores silently, like any unknown prefix):
+/* Two grammar EXTENSIONS (lines the reference ignores silently, like any unknown prefix):
  *   mobj <obj index> <material> <dx> <dy> <dz> <time0> <time1> [t x y z | s x y z | r deg x y z]...
  * = `obj` (scene.h:387-427) whose instance, placed by the transforms at time0, translates by (dx, dy, dz) until
- * time1 -- the instance counterpart of `msphere c0 c1 time0 time1 r material`.
+ * time1 -- the instance counterpart of `msphere c0 c1 time0 time1 r material`;
+ *   kobj <obj index> <material> <time0> <time1> [transforms of the pose at time0]... / [transforms of the pose at time1]...
+ * = an instance KEYFRAMED between two poses (any mix of translation, rotation and scale; the word `/` separates the
+ * two transform lists): every vertex moves linearly from its place in the first pose to its place in the second.
  * On failure *out = NULL and *ref_exit_code (optional) receives the exit code the reference would
  * have used (1, 2, 3 or 4); err/err_len (optional) receive the reference's message. */
 int rrtb_scene_parse_file(const char *path, int image_width, int image_height, rrtb_scene **out,

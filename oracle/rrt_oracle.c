@@ -259,15 +259,34 @@ static f3 triangle_normal(f3 v0, f3 v1, f3 v2)
     return unit3(cross3(unit3(sub3(v1, v0)), unit3(sub3(v2, v0))));
 }
 
-void orc_mtriangle_record(const rrtb_mtriangle *m, float base[3], float rate[3], float e1[3], float e2[3])
+/* include/rrtb.h "rrtb_mtriangle": (base, rate) of v0, e1 = v1 - v0 and e2 = v2 - v0; a zero rate keeps its base exactly */
+static void lin_of(float x_at_time0, float move, float dt, float time0, float *base, float *rate)
+{
+    *rate = move / dt;
+    *base = *rate == 0.0f ? x_at_time0 : fmaf(-*rate, time0, x_at_time0);
+}
+
+void orc_mtriangle_record2(const rrtb_mtriangle *m, float base[3], float rate[3], float e1b[3], float e1r[3], float e2b[3], float e2r[3])
 {
     float dt = m->time1 - m->time0;
     for (int k = 0; k < 3; ++k) {
-        rate[k] = m->delta[k] / dt;
-        base[k] = fmaf(-rate[k], m->time0, m->v0[k]);
-        e1[k] = m->v1[k] - m->v0[k];
-        e2[k] = m->v2[k] - m->v0[k];
+        lin_of(m->v0[k], m->delta[k], dt, m->time0, &base[k], &rate[k]);
+        lin_of(m->v1[k] - m->v0[k], m->extra1[k], dt, m->time0, &e1b[k], &e1r[k]);
+        lin_of(m->v2[k] - m->v0[k], m->extra2[k], dt, m->time0, &e2b[k], &e2r[k]);
     }
+}
+
+/* the edges of the pose at `time` (float): e(t) = fma(rate, t, base); a zero rate keeps its base exactly */
+static f3 edge_at(const float b[3], const float r[3], float time)
+{
+    return F3(r[0] == 0.0f ? b[0] : fmaf(r[0], time, b[0]), r[1] == 0.0f ? b[1] : fmaf(r[1], time, b[1]),
+              r[2] == 0.0f ? b[2] : fmaf(r[2], time, b[2]));
+}
+
+void orc_mtriangle_record(const rrtb_mtriangle *m, float base[3], float rate[3], float e1[3], float e2[3])
+{
+    float e1r[3], e2r[3];
+    orc_mtriangle_record2(m, base, rate, e1, e1r, e2, e2r); /* e1, e2 at time0-extrapolated-to-0: the bases */
 }
 
 void orc_triangle_normal(const rrtb_triangle *tr, float n[3])
@@ -294,12 +313,13 @@ static int hit_t_only(const orc_scene *s, int id, f3 o, f3 d, float time, float 
         return triangle_t(o, d, (double)tr->v0[0], (double)tr->v0[1], (double)tr->v0[2], sub3(ld3(tr->v1), ld3(tr->v0)),
                           sub3(ld3(tr->v2), ld3(tr->v0)), t_min, t_max, t);
     }
-    /* the instance translates, so the ray meets the triangle whose v0 is v0(time); edges unchanged */
-    float base[3], rate[3], e1[3], e2[3];
-    orc_mtriangle_record(&s->mtriangles[r.idx], base, rate, e1, e2);
+    /* the instance moves, so the ray meets the triangle of the pose at its time: v0(time) in double from
+     * the float (base, rate), the edges e1(time), e2(time) in float */
+    float base[3], rate[3], e1b[3], e1r[3], e2b[3], e2r[3];
+    orc_mtriangle_record2(&s->mtriangles[r.idx], base, rate, e1b, e1r, e2b, e2r);
     double tm = (double)time;
     return triangle_t(o, d, fma((double)rate[0], tm, (double)base[0]), fma((double)rate[1], tm, (double)base[1]),
-                      fma((double)rate[2], tm, (double)base[2]), ld3(e1), ld3(e2), t_min, t_max, t);
+                      fma((double)rate[2], tm, (double)base[2]), edge_at(e1b, e1r, time), edge_at(e2b, e2r, time), t_min, t_max, t);
 }
 
 /* hit_record fill: sphere.h:51-55, moving_sphere.h:51-55, triangle.h:62-66, hittable.h:16-20 */
@@ -323,9 +343,11 @@ static void hit_record_fill(const orc_scene *s, int id, f3 o, f3 d, float time, 
         n = triangle_normal(ld3(tr->v0), ld3(tr->v1), ld3(tr->v2));
         *mat = tr->material;
     }
-    else { /* a translation leaves the face normal alone */
+    else { /* the face normal of the pose at the ray's time: unit(cross(unit(e1), unit(e2))), triangle.h:9-15 */
         const rrtb_mtriangle *m = &s->mtriangles[r.idx];
-        n = triangle_normal(ld3(m->v0), ld3(m->v1), ld3(m->v2));
+        float base[3], rate[3], e1b[3], e1r[3], e2b[3], e2r[3];
+        orc_mtriangle_record2(m, base, rate, e1b, e1r, e2b, e2r);
+        n = unit3(cross3(unit3(edge_at(e1b, e1r, time)), unit3(edge_at(e2b, e2r, time))));
         *mat = m->material;
     }
     int front = dot3(d, n) < 0.0f;
@@ -437,14 +459,19 @@ static void prim_box(const orc_scene *s, int id, float *b)
             b[3 + k] = fmaxf(fmaxf(t->v0[k], t->v1[k]), t->v2[k]);
         }
     }
-    else { /* union over the shutter interval of {v0(T), v0(T)+e1, v0(T)+e2}, T = camera time0 / time1 */
-        float base[3], rate[3], e1[3], e2[3];
-        orc_mtriangle_record(&s->mtriangles[r.idx], base, rate, e1, e2);
+    else { /* union of the poses at the two ends of the shutter, T = camera time0 / time1: {v0(T), v0(T)+e1(T), v0(T)+e2(T)};
+            * motion is linear in time, so they bound every pose in between */
+        float base[3], rate[3], e1b[3], e1r[3], e2b[3], e2r[3];
+        orc_mtriangle_record2(&s->mtriangles[r.idx], base, rate, e1b, e1r, e2b, e2r);
+        f3 ea1 = edge_at(e1b, e1r, s->cam.time0), ea2 = edge_at(e2b, e2r, s->cam.time0);
+        f3 eb1 = edge_at(e1b, e1r, s->cam.time1), eb2 = edge_at(e2b, e2r, s->cam.time1);
+        const float a1[3] = {ea1.x, ea1.y, ea1.z}, a2[3] = {ea2.x, ea2.y, ea2.z}, b1[3] = {eb1.x, eb1.y, eb1.z}, b2[3] = {eb2.x, eb2.y, eb2.z};
         for (int k = 0; k < 3; ++k) {
             float pa = fmaf(rate[k], s->cam.time0, base[k]), pb = fmaf(rate[k], s->cam.time1, base[k]);
-            float lo = fminf(pa, pb), hi = fmaxf(pa, pb);
-            b[k] = fminf(fminf(lo, lo + e1[k]), lo + e2[k]);
-            b[3 + k] = fmaxf(fmaxf(hi, hi + e1[k]), hi + e2[k]);
+            float lo = fminf(fminf(fminf(pa, pa + a1[k]), pa + a2[k]), fminf(fminf(pb, pb + b1[k]), pb + b2[k]));
+            float hi = fmaxf(fmaxf(fmaxf(pa, pa + a1[k]), pa + a2[k]), fmaxf(fmaxf(pb, pb + b1[k]), pb + b2[k]));
+            b[k] = lo;
+            b[3 + k] = hi;
         }
     }
 }

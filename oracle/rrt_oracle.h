@@ -91,6 +91,8 @@ void orc_triangle_normal(const rrtb_triangle *tr, float n[3]);
 /* a moving triangle as the product's leaf record defines it (include/rrtb.h "rrtb_mtriangle"):
  * rate[k] = delta[k] / (time1 - time0), base[k] = fma(-rate[k], time0, v0[k]); v0(time) = fma(rate, time, base) */
 void orc_mtriangle_record(const rrtb_mtriangle *m, float base[3], float rate[3], float e1[3], float e2[3]);
+/* the full record: (base, rate) of v0, of e1 = v1 - v0 and of e2 = v2 - v0 (extra1 / extra2 make the edges move) */
+void orc_mtriangle_record2(const rrtb_mtriangle *m, float base[3], float rate[3], float e1b[3], float e1r[3], float e2b[3], float e2r[3]);
 static inline int orc_n_objects(const orc_scene *s) { return s->n_spheres + s->n_mspheres + s->n_triangles + s->n_mtriangles; }
 
 /* ---- the DOUBLE integrator (rrt_oracle_f64.c): FP_T = double semantics over the same float scene ---- */

@@ -147,6 +147,17 @@ static int obj_type(const orc_scene *s, int id)
     return id < s->n_spheres + s->n_mspheres + s->n_triangles ? 2 : 3;
 }
 
+/* (base, rate) of v0 and the float edges e1(time), e2(time) of a moving triangle's pose (include/rrtb.h "rrtb_mtriangle") */
+static void mtri_pose(const rrtb_mtriangle *m, float time, float base[3], float rate[3], float e1[3], float e2[3])
+{
+    float e1b[3], e1r[3], e2b[3], e2r[3];
+    orc_mtriangle_record2(m, base, rate, e1b, e1r, e2b, e2r);
+    for (int k = 0; k < 3; ++k) {
+        e1[k] = e1r[k] == 0.0f ? e1b[k] : fmaf(e1r[k], time, e1b[k]);
+        e2[k] = e2r[k] == 0.0f ? e2b[k] : fmaf(e2r[k], time, e2b[k]);
+    }
+}
+
 static int hit_d(const orc_scene *s, int id, d3 o, d3 d, double time, double t_min, double t_max, double *t)
 {
     int ty = obj_type(s, id);
@@ -167,8 +178,10 @@ static int hit_d(const orc_scene *s, int id, d3 o, d3 d, double time, double t_m
         }
         return triangle_d(o, d, ldf(tr->v0), e1, e2, t_min, t_max, t);
     }
-    float base[3], rate[3], e1[3], e2[3]; /* v0(time) = fma(rate, time, base) */
-    orc_mtriangle_record(&s->mtriangles[id - s->n_spheres - s->n_mspheres - s->n_triangles], base, rate, e1, e2);
+    /* v0(time) = fma(rate, time, base) in double; the edges of the pose at `time` in float from the float
+     * view of the time, as the float integrator evaluates them */
+    float base[3], rate[3], e1[3], e2[3];
+    mtri_pose(&s->mtriangles[id - s->n_spheres - s->n_mspheres - s->n_triangles], (float)time, base, rate, e1, e2);
     d3 v0 = D3(fma((double)rate[0], time, (double)base[0]), fma((double)rate[1], time, (double)base[1]),
                fma((double)rate[2], time, (double)base[2]));
     return triangle_d(o, d, v0, e1, e2, t_min, t_max, t);
@@ -215,12 +228,16 @@ static void record_d(const orc_scene *s, int id, d3 o, d3 d, double time, double
         n = tri_normal_f(tr);
         *mat = tr->material;
     }
-    else {
+    else { /* the float unit normal of the pose at the ray's time */
         const rrtb_mtriangle *m = &s->mtriangles[id - s->n_spheres - s->n_mspheres - s->n_triangles];
+        float base[3], rate[3], e1[3], e2[3];
+        mtri_pose(m, (float)time, base, rate, e1, e2);
         rrtb_triangle tr;
-        memcpy(tr.v0, m->v0, 12);
-        memcpy(tr.v1, m->v1, 12);
-        memcpy(tr.v2, m->v2, 12);
+        for (int k = 0; k < 3; ++k) {
+            tr.v0[k] = 0.0f;
+            tr.v1[k] = e1[k]; /* v1 - v0 = e1 - 0 = e1 exactly */
+            tr.v2[k] = e2[k];
+        }
         n = tri_normal_f(&tr);
         *mat = m->material;
     }

@@ -102,7 +102,7 @@ def load():
     for name in SYMBOLS:
         fn = getattr(lib, name)  # raises AttributeError if the library does not export it
         fn.restype, fn.argtypes = sig[name]
-    if lib.rrtb_abi_version() != 2:
+    if lib.rrtb_abi_version() != 3:
         raise ImportError("rrt_b200: ABI version mismatch")
     _lib = lib
     return lib

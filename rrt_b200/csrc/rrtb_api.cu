@@ -238,6 +238,10 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     if ((rc = dev_reserve(ctx, ctx->d_collapse, (size_t)4))) return rc;
     if ((rc = dev_reserve(ctx, ctx->d_leaves, (size_t)3 * n))) return rc;
     if ((rc = dev_reserve(ctx, ctx->d_leaf_info, (size_t)n))) return rc;
+    if (n_mtriangles > 0) { // edge rates of moving triangles: two float4 per slot, only for scenes that have them
+        if ((rc = dev_reserve(ctx, ctx->d_prim_ext, (size_t)2 * n))) return rc;
+        if ((rc = dev_reserve(ctx, ctx->d_leaf_ext, (size_t)2 * n))) return rc;
+    }
     if ((rc = dev_reserve(ctx, ctx->d_reduce, (size_t)nb * 7 + 16))) return rc;
     if ((rc = dev_reserve(ctx, ctx->d_hist, (size_t)256 * n_seg + (size_t)(256 * n_seg + 4095) / 4096 + 1))) return rc; // + chunk sums
     if ((rc = dev_reserve(ctx, ctx->d_stage, b_sph + b_msph + b_tri + b_mtri))) return rc;
@@ -252,12 +256,17 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     }
 
     // raw structs, staged in one device buffer for k_prepare
+    ctx->stage_off[0] = 0;
+    ctx->stage_off[1] = b_sph;
+    ctx->stage_off[2] = b_sph + b_msph;
+    ctx->stage_off[3] = b_sph + b_msph + b_tri;
     rrtb_sphere *d_sph = (rrtb_sphere *)ctx->d_stage;
     rrtb_msphere *d_msph = (rrtb_msphere *)(ctx->d_stage + b_sph);
     rrtb_triangle *d_tri = (rrtb_triangle *)(ctx->d_stage + b_sph + b_msph);
     rrtb_mtriangle *d_mtri = (rrtb_mtriangle *)(ctx->d_stage + b_sph + b_msph + b_tri);
     cudaStream_t st = ctx->stream;
     RRTB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    if (n_mtriangles > 0) RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_prim_ext, 0, sizeof(float4) * 2 * (size_t)n, st)); // static primitives: no rates
     RRTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_materials, mats.data(), sizeof(float4) * n_materials, cudaMemcpyHostToDevice, st));
     RRTB_CUDA(ctx, cudaMemcpyAsync(ctx->d_material_type, mtypes.data(), sizeof(int) * n_materials, cudaMemcpyHostToDevice, st));
     if (n_spheres)
@@ -285,9 +294,28 @@ int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam)
         ctx->err = "no scene";
         return RRTB_ERR_NO_SCENE;
     }
-    if (ctx->n_mspheres + ctx->n_mtriangles > 0 && (cam->time0 != ctx->cam.time0 || cam->time1 != ctx->cam.time1))
-        return invalid(ctx, "shutter interval changed with moving primitives present: call rrtb_scene_set");
+    // Two things of the acceleration structure depend on the camera: the boxes of moving primitives span its shutter
+    // interval (rrt.cu:169), and the padding of the traversal boxes scales with the largest coordinate a ray can
+    // start from.  When either changes, the LBVH is rebuilt from the raw scene kept on the device (no upload).
+    float mag = 0.f;
+    for (int k = 0; k < 3; ++k) mag = fmaxf(mag, fabsf(cam->origin[k]) + cam->lens_radius);
+    const bool shutter = ctx->n_mspheres + ctx->n_mtriangles > 0 && (cam->time0 != ctx->cam.time0 || cam->time1 != ctx->cam.time1);
+    const bool farther = mag > ctx->build_cam_mag;
     ctx->cam = *cam;
+    if (shutter || farther) {
+        RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
+        ctx->has_scene = false;
+        RRTB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        int rc = prepare_and_build(ctx, (const rrtb_sphere *)(ctx->d_stage + ctx->stage_off[0]), (const rrtb_msphere *)(ctx->d_stage + ctx->stage_off[1]),
+                                   (const rrtb_triangle *)(ctx->d_stage + ctx->stage_off[2]), (const rrtb_mtriangle *)(ctx->d_stage + ctx->stage_off[3]));
+        if (rc) return rc;
+        RRTB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        RRTB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->seconds_build = ms * 1e-3;
+        ctx->has_scene = true;
+    }
     return RRTB_OK;
 }
 

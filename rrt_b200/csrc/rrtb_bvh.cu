@@ -44,12 +44,19 @@ __device__ __forceinline__ float warp_max(float v)
     return v;
 }
 
+// (base, rate) of a coordinate that moves by `move` over dt starting from x at time0; a zero rate keeps x exactly
+__device__ __forceinline__ void lin_of(float x_at_time0, float move, float dt, float time0, float &base, float &rate)
+{
+    rate = __fdiv_rn(move, dt);
+    base = rate == 0.0f ? x_at_time0 : __fmaf_rn(-rate, time0, x_at_time0);
+}
+
 // One thread per object id.  partial[b*7 + 0..2] = centroid min, 3..5 = centroid max, 6 = max |coordinate|
 __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__ sph, int ns,
                                                   const rrtb_msphere *__restrict__ msph, int nms,
                                                   const rrtb_triangle *__restrict__ tri, int nt,
                                                   const rrtb_mtriangle *__restrict__ mtri, int nmt, float cam_t0,
-                                                  float cam_t1, float4 *__restrict__ prim, int2 *__restrict__ info,
+                                                  float cam_t1, float4 *__restrict__ prim, float4 *__restrict__ ext, int2 *__restrict__ info,
                                                   float *__restrict__ prim_box, float *__restrict__ partial)
 {
     const int n = ns + nms + nt + nmt;
@@ -102,24 +109,27 @@ __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__
             c = make_float4(e2[0], e2[1], e2[2], nz);
             mat = t.material;
         }
-        else { // translating instance triangle, include/rrtb.h "rrtb_mtriangle"
+        else { // triangle of a moving instance, include/rrtb.h "rrtb_mtriangle"
             rrtb_mtriangle t = mtri[id - ns - nms - nt];
             float dt = __fsub_rn(t.time1, t.time0);
-            float base[3], rate[3], e1[3], e2[3];
+            float base[3], rate[3], e1b[3], e1r[3], e2b[3], e2r[3];
             for (int k = 0; k < 3; ++k) {
-                rate[k] = __fdiv_rn(t.delta[k], dt);
-                base[k] = __fmaf_rn(-rate[k], t.time0, t.v0[k]);
-                e1[k] = __fsub_rn(t.v1[k], t.v0[k]);
-                e2[k] = __fsub_rn(t.v2[k], t.v0[k]);
-                // union over the shutter interval of {v0(T), v0(T)+e1, v0(T)+e2}, T = camera time0 / time1
+                lin_of(t.v0[k], t.delta[k], dt, t.time0, base[k], rate[k]);
+                lin_of(__fsub_rn(t.v1[k], t.v0[k]), t.extra1[k], dt, t.time0, e1b[k], e1r[k]);
+                lin_of(__fsub_rn(t.v2[k], t.v0[k]), t.extra2[k], dt, t.time0, e2b[k], e2r[k]);
+                // union of the poses at the two ends of the shutter, T = camera time0 / time1: {v0(T), v0(T)+e1(T), v0(T)+e2(T)};
+                // motion is linear in time, so they bound every pose in between
                 float pa = __fmaf_rn(rate[k], cam_t0, base[k]), pb = __fmaf_rn(rate[k], cam_t1, base[k]);
-                float lo = fminf(pa, pb), hi = fmaxf(pa, pb);
-                mn[k] = fminf(fminf(lo, __fadd_rn(lo, e1[k])), __fadd_rn(lo, e2[k]));
-                mx[k] = fmaxf(fmaxf(hi, __fadd_rn(hi, e1[k])), __fadd_rn(hi, e2[k]));
+                float a1 = lin_at(e1r[k], cam_t0, e1b[k]), a2 = lin_at(e2r[k], cam_t0, e2b[k]);
+                float b1 = lin_at(e1r[k], cam_t1, e1b[k]), b2 = lin_at(e2r[k], cam_t1, e2b[k]);
+                mn[k] = fminf(fminf(fminf(pa, __fadd_rn(pa, a1)), __fadd_rn(pa, a2)), fminf(fminf(pb, __fadd_rn(pb, b1)), __fadd_rn(pb, b2)));
+                mx[k] = fmaxf(fmaxf(fmaxf(pa, __fadd_rn(pa, a1)), __fadd_rn(pa, a2)), fmaxf(fmaxf(pb, __fadd_rn(pb, b1)), __fadd_rn(pb, b2)));
             }
             a = make_float4(base[0], base[1], base[2], rate[0]);
-            b = make_float4(e1[0], e1[1], e1[2], rate[1]);
-            c = make_float4(e2[0], e2[1], e2[2], rate[2]);
+            b = make_float4(e1b[0], e1b[1], e1b[2], rate[1]);
+            c = make_float4(e2b[0], e2b[1], e2b[2], rate[2]);
+            ext[2 * id + 0] = make_float4(e1r[0], e1r[1], e1r[2], 0.f);
+            ext[2 * id + 1] = make_float4(e2r[0], e2r[1], e2r[2], 0.f);
             mat = t.material;
         }
         prim[3 * id + 0] = a;
@@ -603,7 +613,8 @@ __global__ void __launch_bounds__(TPB) k_collapse4(const uint64_t *__restrict__ 
 
 __global__ void __launch_bounds__(TPB) k_flatten_leaves(const uint64_t *__restrict__ keys, int n,
                                                          const float4 *__restrict__ prim, const int2 *__restrict__ info,
-                                                         float4 *__restrict__ leaves, int2 *__restrict__ leaf_info)
+                                                         const float4 *__restrict__ prim_ext, float4 *__restrict__ leaves,
+                                                         int2 *__restrict__ leaf_info, float4 *__restrict__ leaf_ext)
 {
     const int k = blockIdx.x * TPB + threadIdx.x;
     if (k >= n) return;
@@ -612,6 +623,10 @@ __global__ void __launch_bounds__(TPB) k_flatten_leaves(const uint64_t *__restri
     leaves[3 * k + 1] = prim[3 * id + 1];
     leaves[3 * k + 2] = prim[3 * id + 2];
     leaf_info[k] = info[id];
+    if (prim_ext) { // scenes with moving triangles: their edge rates follow the record into leaf order
+        leaf_ext[2 * k + 0] = prim_ext[2 * id + 0];
+        leaf_ext[2 * k + 1] = prim_ext[2 * id + 1];
+    }
 }
 
 // exposed to rrtb_api.cu (scene upload): raw struct arrays are staged by the caller
@@ -625,9 +640,10 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
     BuildConsts *bc = (BuildConsts *)(ctx->d_reduce + (size_t)nb * 7);
 
     k_prepare<<<nb, TPB, 0, st>>>(d_sph, ns, d_msph, nms, d_tri, nt, d_mtri, ctx->n_mtriangles, ctx->cam.time0, ctx->cam.time1, ctx->d_prim,
-                                  ctx->d_prim_info, ctx->d_prim_box, ctx->d_reduce);
+                                  ctx->n_mtriangles > 0 ? ctx->d_prim_ext : nullptr, ctx->d_prim_info, ctx->d_prim_box, ctx->d_reduce);
     float cam_mag = 0.f;
     for (int k = 0; k < 3; ++k) cam_mag = fmaxf(cam_mag, fabsf(ctx->cam.origin[k]) + ctx->cam.lens_radius);
+    ctx->build_cam_mag = cam_mag;
     k_bounds<<<1, TPB, 0, st>>>(ctx->d_reduce, nb, cam_mag, bc);
     k_morton<<<nb, TPB, 0, st>>>(ctx->d_prim_box, n, bc, ctx->d_morton, ctx->d_keys);
     RRTB_CUDA(ctx, cudaGetLastError());
@@ -669,8 +685,9 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
     k_collapse4<<<min(want_blocks, ctx->sm_count * 4), TPB, 0, st>>>(ctx->d_keys, n, ns, nms, nt, ctx->d_left, ctx->d_right,
                                                                      ctx->d_prim_box, ctx->d_node_box, bc, ctx->d_wq, cs,
                                                                      ctx->d_wnodes);
-    k_flatten_leaves<<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_prim, ctx->d_prim_info, ctx->d_leaves,
-                                         ctx->d_leaf_info);
+    const bool has_ext = ctx->n_mtriangles > 0;
+    k_flatten_leaves<<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_prim, ctx->d_prim_info, has_ext ? ctx->d_prim_ext : nullptr, ctx->d_leaves,
+                                         ctx->d_leaf_info, has_ext ? ctx->d_leaf_ext : nullptr);
     RRTB_CUDA(ctx, cudaGetLastError());
     return RRTB_OK;
 }
@@ -684,7 +701,7 @@ void free_scene(rrtb_ctx *ctx)
     F(ctx->d_prim); F(ctx->d_prim_info); F(ctx->d_materials); F(ctx->d_material_type); F(ctx->d_prim_box);
     F(ctx->d_morton); F(ctx->d_keys); F(ctx->d_keys_tmp); F(ctx->d_left); F(ctx->d_right); F(ctx->d_parent);
     F(ctx->d_node_box); F(ctx->d_visit); F(ctx->d_wnodes); F(ctx->d_wq); F(ctx->d_collapse); F(ctx->d_leaves);
-    F(ctx->d_leaf_info); F(ctx->d_reduce); F(ctx->d_hist); F(ctx->d_stage);
+    F(ctx->d_leaf_info); F(ctx->d_prim_ext); F(ctx->d_leaf_ext); F(ctx->d_reduce); F(ctx->d_hist); F(ctx->d_stage);
     ctx->capacity.clear();
     ctx->has_scene = false;
 }

@@ -40,8 +40,10 @@ __device__ unsigned int g_rrtb_violations;
 //   sphere         a = (c.xyz, r)
 //   moving sphere  a = (c0.xyz, r)   b = (c1-c0 .xyz, t0)   c = (t1-t0, -, -, -)
 //   triangle       a = (v0.xyz, n.x) b = (e1.xyz, n.y)      c = (e2.xyz, n.z)    n = unit face normal
-//   moving tri.    a = (base.xyz, rate.x) b = (e1.xyz, rate.y) c = (e2.xyz, rate.z)   v0(time) = fma(rate, time, base)
-//                  (include/rrtb.h "rrtb_mtriangle"; the normal is recomputed at shading time)
+//   moving tri.    a = (base.xyz, rate.x) b = (e1 base.xyz, rate.y) c = (e2 base.xyz, rate.z)   v0(time) = fma(rate, time, base)
+//                  + two more float4 in the EXT array (2 per leaf slot, allocated only for scenes with moving triangles):
+//                  x0 = (e1 rate.xyz, -), x1 = (e2 rate.xyz, -);  e(time) = fma(rate, time, base), a zero rate keeps its base
+//                  (include/rrtb.h "rrtb_mtriangle"; the normal is that of the pose at the ray's time)
 // leaf_info[k] = (object id, material index)
 // Traversal node: a 4-WIDE node collapsed from the canonical binary LBVH (rrtb_bvh.cu k_collapse4), 8 x float4
 // (128 B): the padded boxes of the four children as centre c and half extent h, one float4 per component, so that
@@ -59,6 +61,8 @@ struct DeviceScene {
     const int2 *leaf_info;   // [n]
     const float4 *flat_leaves; // [3 * n]  object-id order (scan mode)
     const int2 *flat_info;   // [n]
+    const float4 *leaf_ext;  // [2 * n] edge rates of moving triangles, leaf order (nullptr without moving triangles)
+    const float4 *flat_ext;  // [2 * n] the same in object-id order
     const float4 *materials; // [nm] (albedo.xyz, param)
     const int *material_type;// [nm]
     int n_prims, n_spheres, n_mspheres, n_triangles, n_mtriangles;
@@ -69,6 +73,11 @@ struct DeviceCamera { // rrtb_camera, by value in kernel params (constant bank)
     float origin[3], llc[3], horizontal[3], vertical[3], u[3], v[3], w[3];
     float lens_radius, time0, time1;
     float inv_w1, inv_h1; // 1 / (W - 1), 1 / (H - 1)
+};
+
+struct LeafAux { // what travels with a leaf-record array: (object id, material) per slot, edge rates of moving triangles
+    const int2 *info;
+    const float4 *ext;
 };
 
 struct Ray {
@@ -344,6 +353,23 @@ static __device__ __noinline__ float3 triangle_unit_normal_cold(float4 b, float4
     return n;
 }
 
+// edges of a moving triangle's pose at `time` (include/rrtb.h "rrtb_mtriangle"): e(t) = fma(rate, t, base) in float, a
+// zero rate keeps its base exactly (so a translating instance has bit for bit the edges of the static one)
+__device__ __forceinline__ float lin_at(float rate, float time, float base)
+{
+    return rate == 0.0f ? base : __fmaf_rn(rate, time, base);
+}
+__device__ __forceinline__ void mtri_edges(const float4 *__restrict__ ext, int slot, float time, float4 &b, float4 &c)
+{
+    const float4 x0 = __ldg(ext + 2 * (size_t)(unsigned)slot), x1 = __ldg(ext + 2 * (size_t)(unsigned)slot + 1);
+    b.x = lin_at(x0.x, time, b.x);
+    b.y = lin_at(x0.y, time, b.y);
+    b.z = lin_at(x0.z, time, b.z);
+    c.x = lin_at(x1.x, time, c.x);
+    c.y = lin_at(x1.y, time, c.y);
+    c.z = lin_at(x1.z, time, c.z);
+}
+
 // triangle.h:35-75: Moeller-Trumbore, numerators in double, division-free barycentric tests, exclusive range.
 // (v0x, v0y, v0z) is the first vertex in double: the stored one, or v0(time) of a translating instance triangle.
 __device__ __forceinline__ bool triangle_test(const Ray &r, double v0x, double v0y, double v0z, float4 B, float4 C,
@@ -391,7 +417,7 @@ __device__ __forceinline__ bool candidate_wins(float t, int type, int obj, float
 
 // Test leaf `slot` (type known) and update the running closest hit.
 template <bool COUNT, bool MTRI = true>
-__device__ __forceinline__ void leaf_test(const float4 *__restrict__ leaves, const int2 *__restrict__ info, int slot,
+__device__ __forceinline__ void leaf_test(const float4 *__restrict__ leaves, const LeafAux info, int slot,
                                           int type, const Ray &r, const RayPre &p, float t_min, Hit &best,
                                           TravCounters &cnt)
 {
@@ -416,18 +442,19 @@ __device__ __forceinline__ void leaf_test(const float4 *__restrict__ leaves, con
     else {
         float4 b = __ldg(rec + 1), c = __ldg(rec + 2);
         double v0x = a.x, v0y = a.y, v0z = a.z;
-        if (MTRI && type == PRIM_MTRIANGLE) { // the instance translates: meet the triangle where it is at the ray's time
+        if (MTRI && type == PRIM_MTRIANGLE) { // the instance moves: meet the triangle of the pose at the ray's time
             double tm = r.tm;
             v0x = __fma_rn((double)a.w, tm, v0x);
             v0y = __fma_rn((double)b.w, tm, v0y);
             v0z = __fma_rn((double)c.w, tm, v0z);
+            mtri_edges(info.ext, slot, r.tm, b, c);
         }
         h = triangle_test(r, v0x, v0y, v0z, b, c, t_min, best.t, t);
     }
     if (!h) return;
     if (best.ref >= 0 && t == best.t) { // exact tie: resolve by object id (rare path)
-        int obj = __ldg(&info[slot]).x;
-        int bobj = __ldg(&info[best.ref >> 2]).x;
+        int obj = __ldg(&info.info[slot]).x;
+        int bobj = __ldg(&info.info[best.ref >> 2]).x;
         if (!candidate_wins(t, type, obj, best.t, best.ref & 3, bobj)) return;
     }
     best.t = t;
@@ -446,7 +473,7 @@ __device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, 
     const int n0 = s.n_spheres, n1 = n0 + s.n_mspheres, n2 = n1 + s.n_triangles, n = s.n_prims;
     for (int k = 0; k < n; ++k) {
         int type = k < n0 ? PRIM_SPHERE : (k < n1 ? PRIM_MSPHERE : (k < n2 ? PRIM_TRIANGLE : PRIM_MTRIANGLE));
-        leaf_test<COUNT>(s.flat_leaves, s.flat_info, k, type, r, p, t_min, best, cnt);
+        leaf_test<COUNT>(s.flat_leaves, LeafAux{s.flat_info, s.flat_ext}, k, type, r, p, t_min, best, cnt);
     }
     return best;
 }
@@ -528,7 +555,7 @@ __device__ __forceinline__ void wide_step(const float4 *__restrict__ wnodes, con
 }
 
 template <bool COUNT, bool MTRI = true>
-__device__ __forceinline__ void leaf_step(const float4 *__restrict__ leaves, const int2 *__restrict__ info, const Ray &r,
+__device__ __forceinline__ void leaf_step(const float4 *__restrict__ leaves, const LeafAux info, const Ray &r,
                                           const RayPre &p, float t_min, Hit &best, int &cur, int &sp, const int *stk,
                                           TravCounters &cnt)
 {
@@ -549,7 +576,7 @@ __device__ __forceinline__ Hit closest_bvh(const DeviceScene &s, const Ray &r, c
     int cur = 0;
     while (cur != TRAV_DONE) {
         if (cur >= 0) wide_step<COUNT>(s.wnodes, p, t_min, best.t, cur, sp, stack, cnt);
-        else leaf_step<COUNT>(s.leaves, s.leaf_info, r, p, t_min, best, cur, sp, stack, cnt);
+        else leaf_step<COUNT>(s.leaves, LeafAux{s.leaf_info, s.leaf_ext}, r, p, t_min, best, cur, sp, stack, cnt);
     }
     return best;
 }
@@ -564,7 +591,7 @@ struct HitRecord {
 // MTRI = false compiles the moving-triangle cases out (the pool kernel picks the variant per scene: the dead
 // branches alone cost 1 % on the headline workload)
 template <bool MTRI = true>
-__device__ __forceinline__ HitRecord hit_record(const float4 *__restrict__ leaves, const int2 *__restrict__ info,
+__device__ __forceinline__ HitRecord hit_record(const float4 *__restrict__ leaves, const LeafAux info,
                                                 const Ray &r, const Hit &h)
 {
     HitRecord rec;
@@ -579,8 +606,9 @@ __device__ __forceinline__ HitRecord hit_record(const float4 *__restrict__ leave
         rec.ny = b.w;
         rec.nz = c.w;
     }
-    else if (MTRI && type == PRIM_MTRIANGLE) { // a translation leaves the face normal alone; the record has no room for it
+    else if (MTRI && type == PRIM_MTRIANGLE) { // the face normal of the pose at the ray's time
         float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+        mtri_edges(info.ext, slot, r.tm, b, c);
         float3 n = triangle_unit_normal_cold(b, c);
         rec.nx = n.x;
         rec.ny = n.y;
@@ -604,7 +632,7 @@ __device__ __forceinline__ HitRecord hit_record(const float4 *__restrict__ leave
         rec.ny = -rec.ny;
         rec.nz = -rec.nz;
     }
-    int2 inf = __ldg(&info[slot]);
+    int2 inf = __ldg(&info.info[slot]);
     rec.obj = inf.x;
     rec.mat = inf.y;
     return rec;

@@ -166,7 +166,7 @@ __device__ __forceinline__ bool triangle_test_d(const RayD &r, double v0x, doubl
 }
 
 template <bool COUNT>
-__device__ __forceinline__ void leaf_test_d(const float4 *__restrict__ leaves, const int2 *__restrict__ info, int slot,
+__device__ __forceinline__ void leaf_test_d(const float4 *__restrict__ leaves, const LeafAux info, int slot,
                                             int type, const RayD &r, double t_min, HitD &best, TravCounters &cnt)
 {
     if (COUNT) {
@@ -194,13 +194,14 @@ __device__ __forceinline__ void leaf_test_d(const float4 *__restrict__ leaves, c
             v0x = __fma_rn((double)a.w, r.tm, v0x);
             v0y = __fma_rn((double)b.w, r.tm, v0y);
             v0z = __fma_rn((double)c.w, r.tm, v0z);
+            mtri_edges(info.ext, slot, __double2float_rn(r.tm), b, c); // the float edges of the pose at the float view of the time
         }
         h = triangle_test_d(r, v0x, v0y, v0z, b, c, t_min, best.t, t);
     }
     if (!h) return;
     if (best.ref >= 0 && t == best.t) { // exact tie: the float integrator's rule, by object id
-        int obj = __ldg(&info[slot]).x;
-        int bobj = __ldg(&info[best.ref >> 2]).x;
+        int obj = __ldg(&info.info[slot]).x;
+        int bobj = __ldg(&info.info[best.ref >> 2]).x;
         if (!candidate_wins(0.f, type, obj, 0.f, best.ref & 3, bobj)) return;
     }
     best.t = t;
@@ -216,7 +217,7 @@ __device__ __forceinline__ HitD closest_scan_d(const DeviceScene &s, const RayD 
     const int n0 = s.n_spheres, n1 = n0 + s.n_mspheres, n2 = n1 + s.n_triangles, n = s.n_prims;
     for (int k = 0; k < n; ++k) {
         int type = k < n0 ? PRIM_SPHERE : (k < n1 ? PRIM_MSPHERE : (k < n2 ? PRIM_TRIANGLE : PRIM_MTRIANGLE));
-        leaf_test_d<COUNT>(s.flat_leaves, s.flat_info, k, type, r, t_min, best, cnt);
+        leaf_test_d<COUNT>(s.flat_leaves, LeafAux{s.flat_info, s.flat_ext}, k, type, r, t_min, best, cnt);
     }
     return best;
 }
@@ -239,7 +240,7 @@ __device__ __forceinline__ HitD closest_bvh_d(const DeviceScene &s, const RayD &
             wide_step<COUNT>(s.wnodes, p, t_min_f, __double2float_ru(best.t), cur, sp, stack, cnt);
         }
         else {
-            leaf_test_d<COUNT>(s.leaves, s.leaf_info, (~cur) >> 2, (~cur) & 3, r, t_min, best, cnt);
+            leaf_test_d<COUNT>(s.leaves, LeafAux{s.leaf_info, s.leaf_ext}, (~cur) >> 2, (~cur) & 3, r, t_min, best, cnt);
             trav_pop(cur, sp, stack);
         }
     }
@@ -247,7 +248,7 @@ __device__ __forceinline__ HitD closest_bvh_d(const DeviceScene &s, const RayD &
 }
 
 // ---- hit record: sphere.h:51-55, moving_sphere.h:51-55, triangle.h:62-66, hittable.h:16-20 ---------------
-__device__ __forceinline__ HitRecordD hit_record_d(const float4 *__restrict__ leaves, const int2 *__restrict__ info,
+__device__ __forceinline__ HitRecordD hit_record_d(const float4 *__restrict__ leaves, const LeafAux info,
                                                    const RayD &r, const HitD &h)
 {
     HitRecordD rec;
@@ -264,6 +265,7 @@ __device__ __forceinline__ HitRecordD hit_record_d(const float4 *__restrict__ le
     }
     else if (type == PRIM_MTRIANGLE) {
         float4 b = __ldg(leaves + 3 * slot + 1), c = __ldg(leaves + 3 * slot + 2);
+        mtri_edges(info.ext, slot, __double2float_rn(r.tm), b, c);
         float3 n = triangle_unit_normal_cold(b, c);
         rec.nx = (double)n.x;
         rec.ny = (double)n.y;
@@ -287,7 +289,7 @@ __device__ __forceinline__ HitRecordD hit_record_d(const float4 *__restrict__ le
         rec.ny = -rec.ny;
         rec.nz = -rec.nz;
     }
-    int2 inf = __ldg(&info[slot]);
+    int2 inf = __ldg(&info.info[slot]);
     rec.obj = inf.x;
     rec.mat = inf.y;
     return rec;

@@ -77,6 +77,8 @@ struct ObjInst {
     std::vector<Xform> xf;
     bool moving = false; // `mobj`: translates by delta between time0 and time1
     float delta[3] = {0.f, 0.f, 0.f}, time0 = 0.f, time1 = 1.f;
+    bool keyframed = false; // `kobj`: pose `xf` at time0, pose `xf_end` at time1, vertices move linearly in between
+    std::vector<Xform> xf_end;
 };
 
 struct ParseError {
@@ -313,10 +315,10 @@ int rrtb_scene_parse_file(const char *path, int image_width, int image_height, r
                 objs.push_back(cur);
                 open_obj = false;
             }
-            else if (line.find("obj") == 0 || line.find("mobj") == 0) { // scene.h:387-427; mobj: include/rrtb.h
-                const bool moving = line[0] == 'm';
+            else if (line.find("obj") == 0 || line.find("mobj") == 0 || line.find("kobj") == 0) { // scene.h:387-427; mobj, kobj: include/rrtb.h
+                const bool moving = line[0] == 'm', keyframed = line[0] == 'k';
                 std::vector<std::string> w = words_of(line);
-                if (w.size() < (moving ? 8u : 3u))
+                if (w.size() < (moving ? 8u : (keyframed ? 5u : 3u)))
                     throw ParseError{1, "ERROR: obj called without enough args (count = " + std::to_string(w.size())};
                 ObjInst inst;
                 inst.obj = to_i(w[1]);
@@ -330,18 +332,31 @@ int rrtb_scene_parse_file(const char *path, int image_width, int image_height, r
                     if (!(inst.time1 != inst.time0)) throw ParseError{1, "ERROR: mobj needs time0 != time1"};
                     idx = 8;
                 }
+                if (keyframed) {
+                    inst.moving = inst.keyframed = true;
+                    inst.time0 = to_f(w[3]);
+                    inst.time1 = to_f(w[4]);
+                    if (!(inst.time1 != inst.time0)) throw ParseError{1, "ERROR: kobj needs time0 != time1"};
+                    idx = 5;
+                }
+                std::vector<Xform> *list = &inst.xf;
                 while (idx < w.size() - 1) { // the words vector carries one trailing blank
                     char op = w[idx][0];
-                    if (op == 't' || op == 's') {
+                    if (keyframed && w[idx] == "/") { // the pose at time1 follows
+                        if (list == &inst.xf_end) throw ParseError{1, "ERROR: kobj has more than two poses"};
+                        list = &inst.xf_end;
+                        idx += 1;
+                    }
+                    else if (op == 't' || op == 's') {
                         if (idx + 3 >= w.size()) throw ParseError{1, "ERROR: obj transform needs 3 numbers"};
                         Xform x{op, V3{to_f(w[idx + 1]), to_f(w[idx + 2]), to_f(w[idx + 3])}, 0.0};
-                        inst.xf.push_back(x);
+                        list->push_back(x);
                         idx += 4;
                     }
                     else if (op == 'r') {
                         if (idx + 4 >= w.size()) throw ParseError{1, "ERROR: obj rotate needs angle + axis"};
                         Xform x{'r', V3{to_f(w[idx + 2]), to_f(w[idx + 3]), to_f(w[idx + 4])}, (double)to_f(w[idx + 1])};
-                        inst.xf.push_back(x);
+                        list->push_back(x);
                         idx += 5;
                     }
                     else {
@@ -379,6 +394,19 @@ int rrtb_scene_parse_file(const char *path, int image_width, int image_height, r
                     mt.v1[k] = tr.v1[k];
                     mt.v2[k] = tr.v2[k];
                     mt.delta[k] = in.delta[k];
+                }
+                if (in.keyframed) { // the same triangle in the pose at time1: per-vertex displacements
+                    float end[3][3];
+                    for (int q = 0; q < 3; ++q) {
+                        V3 v = o.verts[o.tris[3 * t + q]];
+                        for (const Xform &x : in.xf_end) v = apply(x, v);
+                        put(end[q], v);
+                    }
+                    for (int k = 0; k < 3; ++k) {
+                        mt.delta[k] = end[0][k] - mt.v0[k];
+                        mt.extra1[k] = (end[1][k] - mt.v1[k]) - mt.delta[k];
+                        mt.extra2[k] = (end[2][k] - mt.v2[k]) - mt.delta[k];
+                    }
                 }
                 mt.time0 = in.time0;
                 mt.time1 = in.time1;

@@ -45,6 +45,8 @@ struct rrtb_ctx {
     int *d_collapse = nullptr;      // CollapseState (wide-node count, ticket, leaves emitted)
     float4 *d_leaves = nullptr;     // [3n] leaf order
     int2 *d_leaf_info = nullptr;    // [n]
+    float4 *d_prim_ext = nullptr;   // [2n] edge rates of moving triangles, object-id order (allocated when the scene has any)
+    float4 *d_leaf_ext = nullptr;   // [2n] the same in leaf order
     // scratch
     float *d_reduce = nullptr;      // block partials + build constants
     unsigned int *d_hist = nullptr; // radix histograms
@@ -53,7 +55,9 @@ struct rrtb_ctx {
     unsigned long long *d_accum = nullptr;    // host-path accumulator (3*W*H)
     float *d_rgb = nullptr;                   // host-path float framebuffer
     size_t accum_elems = 0;
-    unsigned char *d_stage = nullptr;         // raw scene structs of the last upload (input of k_prepare)
+    unsigned char *d_stage = nullptr;         // raw scene structs of the last upload (input of k_prepare; kept for rebuilds)
+    size_t stage_off[4] = {0, 0, 0, 0};       // byte offsets of the sphere / msphere / triangle / mtriangle arrays in d_stage
+    float build_cam_mag = 0.f;                // camera magnitude the traversal-box padding was computed with
     rrtb_render_params pending{};             // the render enqueued by launch_render, for finish_render
     int pending_launches = 0;
     // multi-GPU frame: the owner (rank 0) holds the float/double frame every rank's resolve epilogue stores its

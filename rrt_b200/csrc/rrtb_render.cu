@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 2) k_render(const RenderArgs a)
     const unsigned lane = threadIdx.x & 31u;
     const DeviceScene &s = a.scene;
     const float4 *__restrict__ leaves = USE_BVH ? s.leaves : s.flat_leaves;
-    const int2 *__restrict__ info = USE_BVH ? s.leaf_info : s.flat_info;
+    const LeafAux info = USE_BVH ? LeafAux{s.leaf_info, s.leaf_ext} : LeafAux{s.flat_info, s.flat_ext};
 
     // lane state
     int pixel = -1, ls = 0, ls_end = 0; // current item: pixel, local sample cursor, end
@@ -252,7 +252,7 @@ __global__ void k_trace(const DeviceScene s, const float *__restrict__ rays7, in
     TravCounters tc;
     Hit h = mode ? closest_bvh<false>(s, r, pre, t_min, tc) : closest_scan<false>(s, r, pre, t_min, tc);
     const float4 *leaves = mode ? s.leaves : s.flat_leaves;
-    const int2 *info = mode ? s.leaf_info : s.flat_info;
+    const LeafAux info = mode ? LeafAux{s.leaf_info, s.leaf_ext} : LeafAux{s.flat_info, s.flat_ext};
     if (h.ref < 0) {
         id[i] = -1;
         t[i] = -1.0f;
@@ -364,6 +364,8 @@ DeviceScene device_scene(const rrtb_ctx *ctx)
     s.leaf_info = ctx->d_leaf_info;
     s.flat_leaves = ctx->d_prim;
     s.flat_info = ctx->d_prim_info;
+    s.leaf_ext = ctx->d_leaf_ext;
+    s.flat_ext = ctx->d_prim_ext;
     s.materials = ctx->d_materials;
     s.material_type = ctx->d_material_type;
     s.n_prims = ctx->n_prims;

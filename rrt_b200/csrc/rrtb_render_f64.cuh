@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(RENDER_TPB, 2) k_render_f64(const RenderArgs a
     const unsigned lane = threadIdx.x & 31u;
     const DeviceScene &s = a.scene;
     const float4 *__restrict__ leaves = USE_BVH ? s.leaves : s.flat_leaves;
-    const int2 *__restrict__ info = USE_BVH ? s.leaf_info : s.flat_info;
+    const LeafAux info = USE_BVH ? LeafAux{s.leaf_info, s.leaf_ext} : LeafAux{s.flat_info, s.flat_ext};
 
     int pixel = -1, ls = 0, ls_end = 0;
     unsigned long long acc_r = 0, acc_g = 0, acc_b = 0;
@@ -137,7 +137,7 @@ __global__ void k_trace_f64(const DeviceScene s, const double *__restrict__ rays
             for (int k = 0; k < 7; ++k) rec7[7 * (size_t)i + k] = 0.0;
         return;
     }
-    HitRecordD rec = hit_record_d(mode ? s.leaves : s.flat_leaves, mode ? s.leaf_info : s.flat_info, r, h);
+    HitRecordD rec = hit_record_d(mode ? s.leaves : s.flat_leaves, mode ? LeafAux{s.leaf_info, s.leaf_ext} : LeafAux{s.flat_info, s.flat_ext}, r, h);
     id[i] = rec.obj;
     t[i] = h.t;
     if (rec7) {

@@ -73,13 +73,13 @@ struct PathF32 { // the float integrator (rrtb_device.cuh)
         return h;
     }
     template <bool COUNT, bool MTRI>
-    static __device__ __forceinline__ void leaf(const float4 *__restrict__ leaves, const int2 *__restrict__ info, const Ray &r,
+    static __device__ __forceinline__ void leaf(const float4 *__restrict__ leaves, const LeafAux info, const Ray &r,
                                                 const RayPre &p, Hit &best, int &cur, int &sp, const int *stk, TravCounters &tc)
     {
         leaf_step<COUNT, MTRI>(leaves, info, r, p, 0.001f, best, cur, sp, stk, tc);
     }
     template <bool MTRI>
-    static __device__ __forceinline__ HitRecord record(const float4 *__restrict__ leaves, const int2 *__restrict__ info,
+    static __device__ __forceinline__ HitRecord record(const float4 *__restrict__ leaves, const LeafAux info,
                                                        const Ray &r, const Hit &h)
     {
         return hit_record<MTRI>(leaves, info, r, h);
@@ -127,14 +127,14 @@ struct PathF64 { // the double integrator (rrtb_device_f64.cuh); bit-exact again
         return h;
     }
     template <bool COUNT, bool MTRI>
-    static __device__ __forceinline__ void leaf(const float4 *__restrict__ leaves, const int2 *__restrict__ info, const RayD &r,
+    static __device__ __forceinline__ void leaf(const float4 *__restrict__ leaves, const LeafAux info, const RayD &r,
                                                 const RayPre &, HitD &best, int &cur, int &sp, const int *stk, TravCounters &tc)
     {
         leaf_test_d<COUNT>(leaves, info, (~cur) >> 2, (~cur) & 3, r, 0.001, best, tc);
         trav_pop(cur, sp, stk);
     }
     template <bool MTRI>
-    static __device__ __forceinline__ HitRecordD record(const float4 *__restrict__ leaves, const int2 *__restrict__ info,
+    static __device__ __forceinline__ HitRecordD record(const float4 *__restrict__ leaves, const LeafAux info,
                                                         const RayD &r, const HitD &h)
     {
         return hit_record_d(leaves, info, r, h);
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(RENDER_TPB, P::BLOCKS_PER_SM) k_render_pool(co
     const DeviceScene &s = a.scene;
     const float4 *__restrict__ wnodes = s.wnodes;
     const float4 *__restrict__ leaves = s.leaves;
-    const int2 *__restrict__ info = s.leaf_info;
+    const LeafAux info = {s.leaf_info, s.leaf_ext};
 
     // every slot starts on the gen stack with nothing to accumulate
     for (int k = lane; k < POOL; k += 32) {

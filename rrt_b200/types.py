@@ -31,13 +31,15 @@ msphere_dtype = np.dtype(
     [("center0", "<f4", 3), ("center1", "<f4", 3), ("time0", "<f4"), ("time1", "<f4"), ("radius", "<f4"), ("material", "<i4")]
 )
 triangle_dtype = np.dtype([("v0", "<f4", 3), ("v1", "<f4", 3), ("v2", "<f4", 3), ("material", "<i4")])
-# a triangle of a translating instance (vertices at time0, moves by delta until time1)
+# a triangle of a moving instance (vertices at time0; until time1 vertex 0 moves by delta, vertex 1 by
+# delta + extra1, vertex 2 by delta + extra2 -- extras 0 = translation, include/rrtb.h "rrtb_mtriangle")
 mtriangle_dtype = np.dtype(
-    [("v0", "<f4", 3), ("v1", "<f4", 3), ("v2", "<f4", 3), ("delta", "<f4", 3), ("time0", "<f4"), ("time1", "<f4"), ("material", "<i4")]
+    [("v0", "<f4", 3), ("v1", "<f4", 3), ("v2", "<f4", 3), ("delta", "<f4", 3), ("time0", "<f4"), ("time1", "<f4"), ("material", "<i4"),
+     ("extra1", "<f4", 3), ("extra2", "<f4", 3)]
 )
 
 assert camera_dtype.itemsize == 96
-assert mtriangle_dtype.itemsize == 60
+assert mtriangle_dtype.itemsize == 84
 assert material_dtype.itemsize == 20
 assert sphere_dtype.itemsize == 20
 assert msphere_dtype.itemsize == 40

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for s in syms:
         assert hasattr(lib, s), "librrtb200.so does not export %s" % s
     assert sorted(_lib.SYMBOLS) == syms, "rrt_b200/_lib.py binds a different set than include/rrtb.h declares"
-    assert _lib.load().rrtb_abi_version() == 2
+    assert _lib.load().rrtb_abi_version() == 3
 
 
 def test_struct_layouts_match_header(tmp_path, built_lib):
