@@ -816,7 +816,21 @@ int rrtb_wide_download(rrtb_ctx *ctx, float *nodes, int32_t max_nodes)
     int rc = rrtb_wide_size(ctx, &n_nodes, nullptr);
     if (rc) return rc;
     if (n_nodes > max_nodes) return invalid(ctx, "wide-node buffer too small");
-    RRTB_CUDA(ctx, cudaMemcpy(nodes, ctx->d_wnodes, sizeof(float4) * RRTB_NODE_F4 * (size_t)n_nodes, cudaMemcpyDeviceToHost));
+    // device nodes are 24 words with bf16 half extents (rrtb_device.cuh "Traversal node"); hand them back decoded
+    std::vector<uint32_t> raw((size_t)24 * n_nodes);
+    RRTB_CUDA(ctx, cudaMemcpy(raw.data(), ctx->d_wnodes, sizeof(uint32_t) * raw.size(), cudaMemcpyDeviceToHost));
+    for (int32_t i = 0; i < n_nodes; ++i) {
+        const uint32_t *w = raw.data() + (size_t)24 * i;
+        uint32_t *o = (uint32_t *)nodes + (size_t)32 * i;
+        for (int k = 0; k < 12; ++k) o[k] = w[k];
+        for (int k = 0; k < 6; ++k) { // word 12 + k holds the pair (2 * (k & 1), 2 * (k & 1) + 1) of axis k / 2
+            const int axis = k / 2, c0 = 2 * (k & 1);
+            o[12 + 4 * axis + c0] = w[12 + k] << 16;
+            o[12 + 4 * axis + c0 + 1] = w[12 + k] & 0xffff0000u;
+        }
+        for (int k = 0; k < 4; ++k) o[24 + k] = w[18 + k];
+        for (int k = 0; k < 4; ++k) o[28 + k] = 0;
+    }
     return RRTB_OK;
 }
 

@@ -492,6 +492,17 @@ __global__ void __launch_bounds__(TPB) k_collapse_init(int *__restrict__ wq, int
     }
 }
 
+// half extents travel as bf16 ROUNDED UP (a box may only grow); -inf (unused slot) is exact
+__device__ __forceinline__ unsigned bf16_up(float h)
+{
+    const unsigned b = __float_as_uint(h);
+    return (b & 0x80000000u) ? (b >> 16) : ((b + 0xffffu) >> 16); // h >= 0 (or -inf): next bf16 at or above h
+}
+__device__ __forceinline__ float bf16_pair_up(float lo, float hi)
+{
+    return __uint_as_float(bf16_up(lo) | (bf16_up(hi) << 16));
+}
+
 __device__ __forceinline__ float box_area6(const float *b)
 {
     const float x = b[3] - b[0], y = b[4] - b[1], z = b[5] - b[2];
@@ -559,15 +570,14 @@ __device__ __forceinline__ void collapse_one(int i, int b, const uint64_t *__res
         center_half(bx[1], bx[4], pad, cy[c], hy[c]);
         center_half(bx[2], bx[5], pad, cz[c], hz[c]);
     }
+    // 96-byte node (rrtb_device.cuh "Traversal node"): float centres, bf16 half extents rounded up, refs
     float4 *w = wnodes + RRTB_NODE_F4 * (size_t)i;
     w[0] = make_float4(cx[0], cx[1], cx[2], cx[3]);
     w[1] = make_float4(cy[0], cy[1], cy[2], cy[3]);
     w[2] = make_float4(cz[0], cz[1], cz[2], cz[3]);
-    w[3] = make_float4(hx[0], hx[1], hx[2], hx[3]);
-    w[4] = make_float4(hy[0], hy[1], hy[2], hy[3]);
-    w[5] = make_float4(hz[0], hz[1], hz[2], hz[3]);
-    w[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
-    w[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    w[3] = make_float4(bf16_pair_up(hx[0], hx[1]), bf16_pair_up(hx[2], hx[3]), bf16_pair_up(hy[0], hy[1]), bf16_pair_up(hy[2], hy[3]));
+    w[4] = make_float4(bf16_pair_up(hz[0], hz[1]), bf16_pair_up(hz[2], hz[3]), __int_as_float(ref[0]), __int_as_float(ref[1]));
+    w[5] = make_float4(__int_as_float(ref[2]), __int_as_float(ref[3]), 0.f, 0.f);
     if (leaves) {
         __threadfence(); // the work-list entries written above are visible before the leaf count that ends the polling
         atomicAdd(&st->leaves_done, leaves);

@@ -45,18 +45,22 @@ __device__ unsigned int g_rrtb_violations;
 //                  x0 = (e1 rate.xyz, -), x1 = (e2 rate.xyz, -);  e(time) = fma(rate, time, base), a zero rate keeps its base
 //                  (include/rrtb.h "rrtb_mtriangle"; the normal is that of the pose at the ray's time)
 // leaf_info[k] = (object id, material index)
-// Traversal node: a 4-WIDE node collapsed from the canonical binary LBVH (rrtb_bvh.cu k_collapse4), 8 x float4
-// (128 B): the padded boxes of the four children as centre c and half extent h, one float4 per component, so that
-// one packed FP32x2 instruction (sm_100a FFMA2) works on two children at once and a node is 3 x LDG.E.256 + 1 x
-// LDG.E.128:
-//   w0 = c.x[0..3]  w1 = c.y[0..3]  w2 = c.z[0..3]  w3 = h.x[0..3]  w4 = h.y[0..3]  w5 = h.z[0..3]
-//   w6 = bits(child ref[0..3])      w7 = unused
+// Traversal node: a 4-WIDE node collapsed from the canonical binary LBVH (rrtb_bvh.cu k_collapse4), 24 words (96 B,
+// read with three 256-bit loads): the padded boxes of the four children as centre c (float) and half extent h (bf16,
+// rounded UP: the box only grows, by < 0.8 % of its half extent) and the four child refs:
+//   words  0-11  c.x[0..3]  c.y[0..3]  c.z[0..3]
+//   words 12-17  h.x(0,1) h.x(2,3) h.y(0,1) h.y(2,3) h.z(0,1) h.z(2,3): two bf16 per word, child 2k in the low half --
+//                one shift and one mask turn a word into the FP32x2 pair that FFMA2 takes
+//   words 18-21  bits(child ref[0..3])      words 22-23 unused
+// The render kernels are bound by the l1tex data stage (ncu: 81-87 % of its peak), which spends a cycle per load
+// instruction and 128-byte line touched: the 128-byte all-float node of the first version cost four of them per lane
+// and visit, this one three.
 // child ref >= 0: wide node index;  < 0: leaf, ~ref = (leaf slot << 2) | type.  An unused child slot has
 // h = -inf (its slab test can never pass) and ref = TRAV_DONE.
 enum : int { PRIM_SPHERE = 0, PRIM_MSPHERE = 1, PRIM_TRIANGLE = 2, PRIM_MTRIANGLE = 3 };
 
 struct DeviceScene {
-    const float4 *wnodes;    // [8 * n_wide] 4-wide traversal nodes, root = 0
+    const float4 *wnodes;    // [6 * n_wide] 4-wide traversal nodes (96 B each), root = 0
     const float4 *leaves;    // [3 * n]   leaf order
     const int2 *leaf_info;   // [n]
     const float4 *flat_leaves; // [3 * n]  object-id order (scan mode)
@@ -246,6 +250,13 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
     f32x2 r;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
+}
+
+// two bf16 in one word -> the FP32x2 pair (low half first): a shift and a mask
+__device__ __forceinline__ f32x2 bf16x2(float word)
+{
+    const unsigned w = __float_as_uint(word);
+    return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 
 // Slab test of TWO children of a wide node at once (already padded boxes as centre c and half extent h; each
@@ -495,7 +506,7 @@ __device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, 
 // an index tie-break) and a visit pushes at most three entries, so 192 entries can not overflow; the entries
 // live in local memory (L1-resident).
 #define RRTB_WIDTH 4
-#define RRTB_NODE_F4 (2 * RRTB_WIDTH) // float4 per traversal node
+#define RRTB_NODE_F4 6 // float4 per traversal node (96 B)
 #define RRTB_STACK 192
 #define TRAV_DONE ((int)0x80000000)
 #define KEY_MISS (-1) // as unsigned the largest key, as signed below every real key
@@ -518,20 +529,20 @@ template <bool COUNT>
 __device__ __forceinline__ void wide_step(const float4 *__restrict__ wnodes, const RayPre &p, float t_min, float t_max,
                                           int &cur, int &sp, int *stk, TravCounters &cnt)
 {
-    // the index is widened before it is scaled so that the address is ONE IMAD.WIDE (cur * 128 + base)
+    // the index is widened before it is scaled so that the address is ONE IMAD.WIDE (cur * 96 + base)
     const float4 *q = wnodes + (size_t)(unsigned)cur * (unsigned)RRTB_NODE_F4;
     if (COUNT) cnt.box += RRTB_WIDTH;
-    float4 cx, cy, cz, hx, hy, hz;
-    ldg256(q, cx, cy);
-    ldg256(q + 2, cz, hx);
-    ldg256(q + 4, hy, hz);
-    const int4 rf = __ldg(reinterpret_cast<const int4 *>(q + 6));
+    float4 cx, cy, cz, hw, zr, rs;
+    ldg256(q, cx, cy);     // c.x[4] c.y[4]
+    ldg256(q + 2, cz, hw); // c.z[4], bf16 pairs h.x(0,1) h.x(2,3) h.y(0,1) h.y(2,3)
+    ldg256(q + 4, zr, rs); // bf16 pairs h.z(0,1) h.z(2,3), ref[0..1] | ref[2..3], unused
+    const int4 rf = make_int4(__float_as_int(zr.z), __float_as_int(zr.w), __float_as_int(rs.x), __float_as_int(rs.y));
     bool h0, h1, h2, h3;
     float t0, t1, t2, t3;
-    box_hit_pair(pack2(cx.x, cx.y), pack2(cy.x, cy.y), pack2(cz.x, cz.y), pack2(hx.x, hx.y), pack2(hy.x, hy.y),
-                 pack2(hz.x, hz.y), p, t_min, t_max, h0, h1, t0, t1);
-    box_hit_pair(pack2(cx.z, cx.w), pack2(cy.z, cy.w), pack2(cz.z, cz.w), pack2(hx.z, hx.w), pack2(hy.z, hy.w),
-                 pack2(hz.z, hz.w), p, t_min, t_max, h2, h3, t2, t3);
+    box_hit_pair(pack2(cx.x, cx.y), pack2(cy.x, cy.y), pack2(cz.x, cz.y), bf16x2(hw.x), bf16x2(hw.z), bf16x2(zr.x), p, t_min, t_max,
+                 h0, h1, t0, t1);
+    box_hit_pair(pack2(cx.z, cx.w), pack2(cy.z, cy.w), pack2(cz.z, cz.w), bf16x2(hw.y), bf16x2(hw.w), bf16x2(zr.y), p, t_min, t_max,
+                 h2, h3, t2, t3);
     const int k0 = h0 ? (__float_as_int(t0) & ~3) : KEY_MISS;
     const int k1 = h1 ? ((__float_as_int(t1) & ~3) | 1) : KEY_MISS;
     const int k2 = h2 ? ((__float_as_int(t2) & ~3) | 2) : KEY_MISS;
