@@ -212,6 +212,7 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     ctx->n_mtriangles = n_mtriangles;
     ctx->n_prims = n;
     ctx->use_bvh = use_bvh ? 1 : 0;
+    ctx->motion = n_mspheres + n_mtriangles > 0 && cam->time0 != cam->time1;
 
     int rc;
     const int nb = (n + 255) / 256;
@@ -233,7 +234,11 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     if ((rc = dev_reserve(ctx, ctx->d_parent, (size_t)2 * n))) return rc;
     if ((rc = dev_reserve(ctx, ctx->d_node_box, (size_t)6 * n))) return rc;
     if ((rc = dev_reserve(ctx, ctx->d_visit, (size_t)n))) return rc;
-    if ((rc = dev_reserve(ctx, ctx->d_wnodes, (size_t)RRTB_NODE_F4 * n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_wnodes, (size_t)(n_mspheres + n_mtriangles > 0 ? RRTB_MOTION_NODE_F4 : RRTB_NODE_F4) * n))) return rc;
+    if (n_mspheres + n_mtriangles > 0) { // room for the end-of-shutter boxes whatever this camera's shutter is (rrtb_camera_set may open it)
+        if ((rc = dev_reserve(ctx, ctx->d_prim_box01, (size_t)12 * n))) return rc;
+        if ((rc = dev_reserve(ctx, ctx->d_node_box01, (size_t)12 * n))) return rc;
+    }
     if ((rc = dev_reserve(ctx, ctx->d_wq, (size_t)n))) return rc;
     if ((rc = dev_reserve(ctx, ctx->d_collapse, (size_t)4))) return rc;
     if ((rc = dev_reserve(ctx, ctx->d_leaves, (size_t)3 * n))) return rc;
@@ -302,6 +307,7 @@ int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam)
     const bool shutter = ctx->n_mspheres + ctx->n_mtriangles > 0 && (cam->time0 != ctx->cam.time0 || cam->time1 != ctx->cam.time1);
     const bool farther = mag > ctx->build_cam_mag;
     ctx->cam = *cam;
+    ctx->motion = ctx->n_mspheres + ctx->n_mtriangles > 0 && cam->time0 != cam->time1;
     if (shutter || farther) {
         RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
         ctx->has_scene = false;
@@ -816,20 +822,39 @@ int rrtb_wide_download(rrtb_ctx *ctx, float *nodes, int32_t max_nodes)
     int rc = rrtb_wide_size(ctx, &n_nodes, nullptr);
     if (rc) return rc;
     if (n_nodes > max_nodes) return invalid(ctx, "wide-node buffer too small");
-    // device nodes are 24 words with bf16 half extents (rrtb_device.cuh "Traversal node"); hand them back decoded
-    std::vector<uint32_t> raw((size_t)24 * n_nodes);
+    // device nodes are 24 words with bf16 half extents (rrtb_device.cuh "Traversal node"), or 40 words with the boxes at
+    // both ends of the shutter ("Motion node"); hand them back decoded, the motion node as the UNION of its two boxes
+    const int words = ctx->motion ? 40 : 24;
+    std::vector<uint32_t> raw((size_t)words * n_nodes);
     RRTB_CUDA(ctx, cudaMemcpy(raw.data(), ctx->d_wnodes, sizeof(uint32_t) * raw.size(), cudaMemcpyDeviceToHost));
+    auto f = [](uint32_t b) {
+        float x;
+        memcpy(&x, &b, 4);
+        return x;
+    };
     for (int32_t i = 0; i < n_nodes; ++i) {
-        const uint32_t *w = raw.data() + (size_t)24 * i;
-        uint32_t *o = (uint32_t *)nodes + (size_t)32 * i;
-        for (int k = 0; k < 12; ++k) o[k] = w[k];
-        for (int k = 0; k < 6; ++k) { // word 12 + k holds the pair (2 * (k & 1), 2 * (k & 1) + 1) of axis k / 2
-            const int axis = k / 2, c0 = 2 * (k & 1);
-            o[12 + 4 * axis + c0] = w[12 + k] << 16;
-            o[12 + 4 * axis + c0 + 1] = w[12 + k] & 0xffff0000u;
-        }
-        for (int k = 0; k < 4; ++k) o[24 + k] = w[18 + k];
-        for (int k = 0; k < 4; ++k) o[28 + k] = 0;
+        const uint32_t *w = raw.data() + (size_t)words * i;
+        float *o = nodes + (size_t)32 * i;
+        const int hbase = ctx->motion ? 24 : 12, rbase = ctx->motion ? 36 : 18;
+        for (int axis = 0; axis < 3; ++axis)
+            for (int c = 0; c < 4; ++c) {
+                const int pw = 2 * axis + c / 2; // the pair word of (axis, child pair)
+                auto half = [&](int base) { return (c & 1) ? f(w[base + pw] & 0xffff0000u) : f(w[base + pw] << 16); };
+                float c0 = f(w[4 * axis + c]), h0 = half(hbase);
+                if (ctx->motion) {
+                    const float c1 = f(w[12 + 4 * axis + c]), h1 = half(hbase + 6);
+                    const float lo = fminf(c0 - h0, c1 - h1), hi = fmaxf(c0 + h0, c1 + h1);
+                    if (h0 == -INFINITY) h0 = -INFINITY; // unused slot stays unused
+                    else {
+                        c0 = 0.5f * (lo + hi);
+                        h0 = fmaxf(hi - c0, c0 - lo);
+                    }
+                }
+                o[4 * axis + c] = c0;
+                o[12 + 4 * axis + c] = h0;
+            }
+        for (int k = 0; k < 4; ++k) memcpy(&o[24 + k], &w[rbase + k], 4);
+        for (int k = 0; k < 4; ++k) o[28 + k] = 0.f;
     }
     return RRTB_OK;
 }

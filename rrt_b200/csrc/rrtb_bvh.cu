@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__
                                                   const rrtb_triangle *__restrict__ tri, int nt,
                                                   const rrtb_mtriangle *__restrict__ mtri, int nmt, float cam_t0,
                                                   float cam_t1, float4 *__restrict__ prim, float4 *__restrict__ ext, int2 *__restrict__ info,
-                                                  float *__restrict__ prim_box, float *__restrict__ partial)
+                                                  float *__restrict__ prim_box, float *__restrict__ prim_box01,
+                                                  float *__restrict__ partial)
 {
     const int n = ns + nms + nt + nmt;
     const int id = blockIdx.x * TPB + threadIdx.x;
@@ -66,6 +67,10 @@ __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__
     if (id < n) {
         float4 a, b = make_float4(0, 0, 0, 0), c = make_float4(0, 0, 0, 0);
         int mat;
+        // boxes of the primitive at the two ENDS of the shutter (prim_box01, scenes with motion only): lo/hi at camera
+        // time0 in e0, at time1 in e1; static primitives fill them from their one box below
+        float e0[6], e1x[6];
+        bool moving = false;
         if (id < ns) {
             rrtb_sphere s = sph[id];
             a = make_float4(s.center[0], s.center[1], s.center[2], s.radius);
@@ -87,7 +92,12 @@ __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__
                 float cb = __fadd_rn(m.center0[k], __fmul_rn(k1, dc[k]));
                 mn[k] = fminf(__fsub_rn(ca, m.radius), __fsub_rn(cb, m.radius));
                 mx[k] = fmaxf(__fadd_rn(ca, m.radius), __fadd_rn(cb, m.radius));
+                e0[k] = __fsub_rn(ca, m.radius);
+                e0[3 + k] = __fadd_rn(ca, m.radius);
+                e1x[k] = __fsub_rn(cb, m.radius);
+                e1x[3 + k] = __fadd_rn(cb, m.radius);
             }
+            moving = true;
             a = make_float4(m.center0[0], m.center0[1], m.center0[2], m.radius);
             b = make_float4(dc[0], dc[1], dc[2], m.time0);
             c = make_float4(dt, 0.f, 0.f, 0.f);
@@ -122,9 +132,14 @@ __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__
                 float pa = __fmaf_rn(rate[k], cam_t0, base[k]), pb = __fmaf_rn(rate[k], cam_t1, base[k]);
                 float a1 = lin_at(e1r[k], cam_t0, e1b[k]), a2 = lin_at(e2r[k], cam_t0, e2b[k]);
                 float b1 = lin_at(e1r[k], cam_t1, e1b[k]), b2 = lin_at(e2r[k], cam_t1, e2b[k]);
-                mn[k] = fminf(fminf(fminf(pa, __fadd_rn(pa, a1)), __fadd_rn(pa, a2)), fminf(fminf(pb, __fadd_rn(pb, b1)), __fadd_rn(pb, b2)));
-                mx[k] = fmaxf(fmaxf(fmaxf(pa, __fadd_rn(pa, a1)), __fadd_rn(pa, a2)), fmaxf(fmaxf(pb, __fadd_rn(pb, b1)), __fadd_rn(pb, b2)));
+                e0[k] = fminf(fminf(pa, __fadd_rn(pa, a1)), __fadd_rn(pa, a2));
+                e0[3 + k] = fmaxf(fmaxf(pa, __fadd_rn(pa, a1)), __fadd_rn(pa, a2));
+                e1x[k] = fminf(fminf(pb, __fadd_rn(pb, b1)), __fadd_rn(pb, b2));
+                e1x[3 + k] = fmaxf(fmaxf(pb, __fadd_rn(pb, b1)), __fadd_rn(pb, b2));
+                mn[k] = fminf(e0[k], e1x[k]);
+                mx[k] = fmaxf(e0[3 + k], e1x[3 + k]);
             }
+            moving = true;
             a = make_float4(base[0], base[1], base[2], rate[0]);
             b = make_float4(e1b[0], e1b[1], e1b[2], rate[1]);
             c = make_float4(e2b[0], e2b[1], e2b[2], rate[2]);
@@ -140,6 +155,13 @@ __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__
             prim_box[6 * id + k] = mn[k];
             prim_box[6 * id + 3 + k] = mx[k];
         }
+        if (prim_box01)
+            for (int k = 0; k < 3; ++k) {
+                prim_box01[12 * id + k] = moving ? e0[k] : mn[k];
+                prim_box01[12 * id + 3 + k] = moving ? e0[3 + k] : mx[k];
+                prim_box01[12 * id + 6 + k] = moving ? e1x[k] : mn[k];
+                prim_box01[12 * id + 9 + k] = moving ? e1x[3 + k] : mx[k];
+            }
     }
     // block reduction of centroid bounds and coordinate magnitude
     float v[7];
@@ -423,7 +445,10 @@ __global__ void __launch_bounds__(TPB) k_karras(const uint64_t *__restrict__ key
     if (i == 0) parent[0] = -1;
 }
 
-// one thread per leaf climbs; the second thread to reach a node computes its box
+// one thread per leaf climbs; the second thread to reach a node computes its box.  NB boxes per entry: 1 = the canonical
+// box (union over the shutter), 2 = the boxes at the two ends of the shutter (scenes with motion: the traversal nodes
+// interpolate between them)
+template <int NB>
 __global__ void __launch_bounds__(TPB) k_refit(const uint64_t *__restrict__ keys, int n,
                                                 const int *__restrict__ left, const int *__restrict__ right,
                                                 const int *__restrict__ parent, const float *__restrict__ prim_box,
@@ -438,16 +463,18 @@ __global__ void __launch_bounds__(TPB) k_refit(const uint64_t *__restrict__ keys
         if (atomicAdd(&visit[node], 1) == 0) return;
         __threadfence();
         const int L = left[node], R = right[node];
-        const volatile float *lb = L >= 0 ? node_box + 6 * L : nullptr;
-        const volatile float *rb = R >= 0 ? node_box + 6 * R : nullptr;
-        float l6[6], r6[6];
-        for (int c = 0; c < 6; ++c) {
-            l6[c] = L >= 0 ? lb[c] : prim_box[6 * (uint32_t)keys[~L] + c];
-            r6[c] = R >= 0 ? rb[c] : prim_box[6 * (uint32_t)keys[~R] + c];
-        }
-        for (int c = 0; c < 3; ++c) {
-            node_box[6 * node + c] = fminf(l6[c], r6[c]);
-            node_box[6 * node + 3 + c] = fmaxf(l6[3 + c], r6[3 + c]);
+        const volatile float *lb = L >= 0 ? node_box + 6 * NB * L : nullptr;
+        const volatile float *rb = R >= 0 ? node_box + 6 * NB * R : nullptr;
+        for (int e = 0; e < NB; ++e) {
+            float l6[6], r6[6];
+            for (int c = 0; c < 6; ++c) {
+                l6[c] = L >= 0 ? lb[6 * e + c] : prim_box[6 * NB * (uint32_t)keys[~L] + 6 * e + c];
+                r6[c] = R >= 0 ? rb[6 * e + c] : prim_box[6 * NB * (uint32_t)keys[~R] + 6 * e + c];
+            }
+            for (int c = 0; c < 3; ++c) {
+                node_box[6 * NB * node + 6 * e + c] = fminf(l6[c], r6[c]);
+                node_box[6 * NB * node + 6 * e + 3 + c] = fmaxf(l6[3 + c], r6[3 + c]);
+            }
         }
         node = parent[node];
     }
@@ -512,6 +539,7 @@ __device__ __forceinline__ float box_area6(const float *b)
 __device__ __forceinline__ void collapse_one(int i, int b, const uint64_t *__restrict__ keys, int n, int ns, int nms, int nt,
                                              const int *__restrict__ left, const int *__restrict__ right,
                                              const float *__restrict__ prim_box, const float *__restrict__ node_box,
+                                             const float *__restrict__ prim_box01, const float *__restrict__ node_box01,
                                              float pad, int *wq, CollapseState *st, float4 *__restrict__ wnodes)
 {
     constexpr int WD = RRTB_WIDTH;
@@ -543,12 +571,14 @@ __device__ __forceinline__ void collapse_one(int i, int b, const uint64_t *__res
         }
     }
     float cx[WD], cy[WD], cz[WD], hx[WD], hy[WD], hz[WD];
+    float c1x[WD], c1y[WD], c1z[WD], h1x[WD], h1y[WD], h1z[WD]; // motion nodes: the box at the END of the shutter
     int ref[WD];
     int leaves = 0;
+    const bool motion = prim_box01 != nullptr;
     for (int c = 0; c < WD; ++c) {
         if (c >= nc) { // unused slot: never hit
-            cx[c] = cy[c] = cz[c] = 0.f;
-            hx[c] = hy[c] = hz[c] = -__int_as_float(0x7f800000);
+            cx[c] = cy[c] = cz[c] = c1x[c] = c1y[c] = c1z[c] = 0.f;
+            hx[c] = hy[c] = hz[c] = h1x[c] = h1y[c] = h1z[c] = -__int_as_float(0x7f800000);
             ref[c] = TRAV_DONE;
             continue;
         }
@@ -557,27 +587,49 @@ __device__ __forceinline__ void collapse_one(int i, int b, const uint64_t *__res
             const int j = atomicAdd(&st->n_alloc, 1);
             *(volatile int *)(wq + j) = ch[c];
             ref[c] = j;
-            bx = node_box + 6 * ch[c];
+            bx = motion ? node_box01 + 12 * ch[c] : node_box + 6 * ch[c];
         }
         else {
             const int slot = ~ch[c];
             const int id = (int)(uint32_t)keys[slot];
             ref[c] = ~((slot << 2) | prim_type(id, ns, nms, nt));
-            bx = prim_box + 6 * id;
+            bx = motion ? prim_box01 + 12 * id : prim_box + 6 * id;
             ++leaves;
         }
         center_half(bx[0], bx[3], pad, cx[c], hx[c]);
         center_half(bx[1], bx[4], pad, cy[c], hy[c]);
         center_half(bx[2], bx[5], pad, cz[c], hz[c]);
+        if (motion) {
+            center_half(bx[6], bx[9], pad, c1x[c], h1x[c]);
+            center_half(bx[7], bx[10], pad, c1y[c], h1y[c]);
+            center_half(bx[8], bx[11], pad, c1z[c], h1z[c]);
+        }
     }
-    // 96-byte node (rrtb_device.cuh "Traversal node"): float centres, bf16 half extents rounded up, refs
-    float4 *w = wnodes + RRTB_NODE_F4 * (size_t)i;
-    w[0] = make_float4(cx[0], cx[1], cx[2], cx[3]);
-    w[1] = make_float4(cy[0], cy[1], cy[2], cy[3]);
-    w[2] = make_float4(cz[0], cz[1], cz[2], cz[3]);
-    w[3] = make_float4(bf16_pair_up(hx[0], hx[1]), bf16_pair_up(hx[2], hx[3]), bf16_pair_up(hy[0], hy[1]), bf16_pair_up(hy[2], hy[3]));
-    w[4] = make_float4(bf16_pair_up(hz[0], hz[1]), bf16_pair_up(hz[2], hz[3]), __int_as_float(ref[0]), __int_as_float(ref[1]));
-    w[5] = make_float4(__int_as_float(ref[2]), __int_as_float(ref[3]), 0.f, 0.f);
+    if (motion) {
+        // 160-byte motion node (rrtb_device.cuh "Motion node"): centres at both ends of the shutter, bf16 half extents
+        // (rounded up) at both ends, refs; the traversal interpolates box(s) = (1 - s) box0 + s box1
+        float4 *w = wnodes + RRTB_MOTION_NODE_F4 * (size_t)i;
+        w[0] = make_float4(cx[0], cx[1], cx[2], cx[3]);
+        w[1] = make_float4(cy[0], cy[1], cy[2], cy[3]);
+        w[2] = make_float4(cz[0], cz[1], cz[2], cz[3]);
+        w[3] = make_float4(c1x[0], c1x[1], c1x[2], c1x[3]);
+        w[4] = make_float4(c1y[0], c1y[1], c1y[2], c1y[3]);
+        w[5] = make_float4(c1z[0], c1z[1], c1z[2], c1z[3]);
+        w[6] = make_float4(bf16_pair_up(hx[0], hx[1]), bf16_pair_up(hx[2], hx[3]), bf16_pair_up(hy[0], hy[1]), bf16_pair_up(hy[2], hy[3]));
+        w[7] = make_float4(bf16_pair_up(hz[0], hz[1]), bf16_pair_up(hz[2], hz[3]), bf16_pair_up(h1x[0], h1x[1]), bf16_pair_up(h1x[2], h1x[3]));
+        w[8] = make_float4(bf16_pair_up(h1y[0], h1y[1]), bf16_pair_up(h1y[2], h1y[3]), bf16_pair_up(h1z[0], h1z[1]), bf16_pair_up(h1z[2], h1z[3]));
+        w[9] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
+    }
+    else {
+        // 96-byte node (rrtb_device.cuh "Traversal node"): float centres, bf16 half extents rounded up, refs
+        float4 *w = wnodes + RRTB_NODE_F4 * (size_t)i;
+        w[0] = make_float4(cx[0], cx[1], cx[2], cx[3]);
+        w[1] = make_float4(cy[0], cy[1], cy[2], cy[3]);
+        w[2] = make_float4(cz[0], cz[1], cz[2], cz[3]);
+        w[3] = make_float4(bf16_pair_up(hx[0], hx[1]), bf16_pair_up(hx[2], hx[3]), bf16_pair_up(hy[0], hy[1]), bf16_pair_up(hy[2], hy[3]));
+        w[4] = make_float4(bf16_pair_up(hz[0], hz[1]), bf16_pair_up(hz[2], hz[3]), __int_as_float(ref[0]), __int_as_float(ref[1]));
+        w[5] = make_float4(__int_as_float(ref[2]), __int_as_float(ref[3]), 0.f, 0.f);
+    }
     if (leaves) {
         __threadfence(); // the work-list entries written above are visible before the leaf count that ends the polling
         atomicAdd(&st->leaves_done, leaves);
@@ -587,6 +639,7 @@ __device__ __forceinline__ void collapse_one(int i, int b, const uint64_t *__res
 __global__ void __launch_bounds__(TPB) k_collapse4(const uint64_t *__restrict__ keys, int n, int ns, int nms, int nt,
                                                     const int *__restrict__ left, const int *__restrict__ right,
                                                     const float *__restrict__ prim_box, const float *__restrict__ node_box,
+                                                    const float *__restrict__ prim_box01, const float *__restrict__ node_box01,
                                                     const BuildConsts *__restrict__ bc, int *wq, CollapseState *st,
                                                     float4 *__restrict__ wnodes)
 {
@@ -612,7 +665,7 @@ __global__ void __launch_bounds__(TPB) k_collapse4(const uint64_t *__restrict__ 
                     }
                 }
                 if (b >= 0) {
-                    collapse_one(i, b, keys, n, ns, nms, nt, left, right, prim_box, node_box, pad, wq, st, wnodes);
+                    collapse_one(i, b, keys, n, ns, nms, nt, left, right, prim_box, node_box, prim_box01, node_box01, pad, wq, st, wnodes);
                     pending = false;
                 }
             }
@@ -650,7 +703,8 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
     BuildConsts *bc = (BuildConsts *)(ctx->d_reduce + (size_t)nb * 7);
 
     k_prepare<<<nb, TPB, 0, st>>>(d_sph, ns, d_msph, nms, d_tri, nt, d_mtri, ctx->n_mtriangles, ctx->cam.time0, ctx->cam.time1, ctx->d_prim,
-                                  ctx->n_mtriangles > 0 ? ctx->d_prim_ext : nullptr, ctx->d_prim_info, ctx->d_prim_box, ctx->d_reduce);
+                                  ctx->n_mtriangles > 0 ? ctx->d_prim_ext : nullptr, ctx->d_prim_info, ctx->d_prim_box,
+                                  ctx->motion ? ctx->d_prim_box01 : nullptr, ctx->d_reduce);
     float cam_mag = 0.f;
     for (int k = 0; k < 3; ++k) cam_mag = fmaxf(cam_mag, fabsf(ctx->cam.origin[k]) + ctx->cam.lens_radius);
     ctx->build_cam_mag = cam_mag;
@@ -682,8 +736,13 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
         const int nbi = (n - 1 + TPB - 1) / TPB;
         RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_visit, 0, sizeof(int) * (size_t)(n - 1), st));
         k_karras<<<nbi, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left, ctx->d_right, ctx->d_parent);
-        k_refit<<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_prim_box,
-                                    ctx->d_node_box, ctx->d_visit);
+        k_refit<1><<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_prim_box,
+                                       ctx->d_node_box, ctx->d_visit);
+        if (ctx->motion) { // boxes at the two ends of the shutter, for the interpolating traversal nodes
+            RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_visit, 0, sizeof(int) * (size_t)(n - 1), st));
+            k_refit<2><<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_prim_box01,
+                                           ctx->d_node_box01, ctx->d_visit);
+        }
     }
     else {
         int m1 = -1;
@@ -693,8 +752,8 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
     k_collapse_init<<<nb, TPB, 0, st>>>(ctx->d_wq, n, cs);
     const int want_blocks = (max(n - 1, 1) + TPB - 1) / TPB;
     k_collapse4<<<min(want_blocks, ctx->sm_count * 4), TPB, 0, st>>>(ctx->d_keys, n, ns, nms, nt, ctx->d_left, ctx->d_right,
-                                                                     ctx->d_prim_box, ctx->d_node_box, bc, ctx->d_wq, cs,
-                                                                     ctx->d_wnodes);
+                                                                     ctx->d_prim_box, ctx->d_node_box, ctx->motion ? ctx->d_prim_box01 : nullptr,
+                                                                     ctx->motion ? ctx->d_node_box01 : nullptr, bc, ctx->d_wq, cs, ctx->d_wnodes);
     const bool has_ext = ctx->n_mtriangles > 0;
     k_flatten_leaves<<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_prim, ctx->d_prim_info, has_ext ? ctx->d_prim_ext : nullptr, ctx->d_leaves,
                                          ctx->d_leaf_info, has_ext ? ctx->d_leaf_ext : nullptr);
@@ -711,7 +770,7 @@ void free_scene(rrtb_ctx *ctx)
     F(ctx->d_prim); F(ctx->d_prim_info); F(ctx->d_materials); F(ctx->d_material_type); F(ctx->d_prim_box);
     F(ctx->d_morton); F(ctx->d_keys); F(ctx->d_keys_tmp); F(ctx->d_left); F(ctx->d_right); F(ctx->d_parent);
     F(ctx->d_node_box); F(ctx->d_visit); F(ctx->d_wnodes); F(ctx->d_wq); F(ctx->d_collapse); F(ctx->d_leaves);
-    F(ctx->d_leaf_info); F(ctx->d_prim_ext); F(ctx->d_leaf_ext); F(ctx->d_reduce); F(ctx->d_hist); F(ctx->d_stage);
+    F(ctx->d_leaf_info); F(ctx->d_prim_ext); F(ctx->d_leaf_ext); F(ctx->d_prim_box01); F(ctx->d_node_box01); F(ctx->d_reduce); F(ctx->d_hist); F(ctx->d_stage);
     ctx->capacity.clear();
     ctx->has_scene = false;
 }

@@ -57,10 +57,20 @@ __device__ unsigned int g_rrtb_violations;
 // and visit, this one three.
 // child ref >= 0: wide node index;  < 0: leaf, ~ref = (leaf slot << 2) | type.  An unused child slot has
 // h = -inf (its slab test can never pass) and ref = TRAV_DONE.
+//
+// Motion node (scenes with moving primitives and an open shutter): 40 words (160 B, five 256-bit loads):
+// the child boxes at BOTH ends of the shutter; the traversal interpolates box(s) = (1 - s) box0 + s box1 with
+// s = (ray time - shutter open) / (shutter close - open).  Primitives move linearly in time, so the interpolated
+// box bounds them at every time of the shutter and is as tight as the motion allows, where a box spanning the whole
+// shutter (the reference's moving_sphere::bounding_box, moving_sphere.h:60-66) grows with the distance travelled.
+//   words  0-11  c0.x[4] c0.y[4] c0.z[4]        words 12-23  c1.x[4] c1.y[4] c1.z[4]
+//   words 24-29  h0 pairs (as above)             words 30-35  h1 pairs        words 36-39  bits(child ref[0..3])
 enum : int { PRIM_SPHERE = 0, PRIM_MSPHERE = 1, PRIM_TRIANGLE = 2, PRIM_MTRIANGLE = 3 };
 
 struct DeviceScene {
-    const float4 *wnodes;    // [6 * n_wide] 4-wide traversal nodes (96 B each), root = 0
+    const float4 *wnodes;    // [6 * n_wide] 4-wide traversal nodes (96 B each), root = 0; motion: [10 * n_wide] (160 B)
+    int motion;              // != 0: wnodes holds motion nodes
+    float shutter_open, shutter_inv; // s = (time - shutter_open) * shutter_inv
     const float4 *leaves;    // [3 * n]   leaf order
     const int2 *leaf_info;   // [n]
     const float4 *flat_leaves; // [3 * n]  object-id order (scan mode)
@@ -176,6 +186,7 @@ __device__ __forceinline__ Ray camera_ray(const DeviceCamera &cam, int W, int H,
 struct RayPre {
     float ix, iy, iz;    // ~1/d
     float oox, ooy, ooz; // -o/d
+    float s;             // motion nodes only: where the ray's time lies in the shutter interval, 0 .. 1
 };
 
 __device__ __forceinline__ float rcp_approx(float x)
@@ -195,6 +206,7 @@ __device__ __forceinline__ RayPre ray_pre(const Ray &r)
     p.oox = -r.ox * p.ix;
     p.ooy = -r.oy * p.iy;
     p.ooz = -r.oz * p.iz;
+    p.s = 0.f;
     return p;
 }
 
@@ -507,6 +519,7 @@ __device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, 
 // live in local memory (L1-resident).
 #define RRTB_WIDTH 4
 #define RRTB_NODE_F4 6 // float4 per traversal node (96 B)
+#define RRTB_MOTION_NODE_F4 10 // float4 per motion node (160 B)
 #define RRTB_STACK 192
 #define TRAV_DONE ((int)0x80000000)
 #define KEY_MISS (-1) // as unsigned the largest key, as signed below every real key
@@ -525,24 +538,50 @@ __device__ __forceinline__ void trav_pop(int &cur, int &sp, const int *stk)
 }
 
 // t_min must be >= 0 (keys order as integers only for non-negative distances); rrtb_trace_closest checks it
-template <bool COUNT>
+// (1 - s) a + s b on an FP32x2 pair
+__device__ __forceinline__ f32x2 lerp2(f32x2 a, f32x2 b, float s, float oms)
+{
+    return fma2(b, pack2(s, s), mul2(a, pack2(oms, oms)));
+}
+
+template <bool COUNT, bool MOTION = false>
 __device__ __forceinline__ void wide_step(const float4 *__restrict__ wnodes, const RayPre &p, float t_min, float t_max,
                                           int &cur, int &sp, int *stk, TravCounters &cnt)
 {
-    // the index is widened before it is scaled so that the address is ONE IMAD.WIDE (cur * 96 + base)
-    const float4 *q = wnodes + (size_t)(unsigned)cur * (unsigned)RRTB_NODE_F4;
     if (COUNT) cnt.box += RRTB_WIDTH;
-    float4 cx, cy, cz, hw, zr, rs;
-    ldg256(q, cx, cy);     // c.x[4] c.y[4]
-    ldg256(q + 2, cz, hw); // c.z[4], bf16 pairs h.x(0,1) h.x(2,3) h.y(0,1) h.y(2,3)
-    ldg256(q + 4, zr, rs); // bf16 pairs h.z(0,1) h.z(2,3), ref[0..1] | ref[2..3], unused
-    const int4 rf = make_int4(__float_as_int(zr.z), __float_as_int(zr.w), __float_as_int(rs.x), __float_as_int(rs.y));
     bool h0, h1, h2, h3;
     float t0, t1, t2, t3;
-    box_hit_pair(pack2(cx.x, cx.y), pack2(cy.x, cy.y), pack2(cz.x, cz.y), bf16x2(hw.x), bf16x2(hw.z), bf16x2(zr.x), p, t_min, t_max,
-                 h0, h1, t0, t1);
-    box_hit_pair(pack2(cx.z, cx.w), pack2(cy.z, cy.w), pack2(cz.z, cz.w), bf16x2(hw.y), bf16x2(hw.w), bf16x2(zr.y), p, t_min, t_max,
-                 h2, h3, t2, t3);
+    int4 rf;
+    if (MOTION) {
+        const float4 *q = wnodes + (size_t)(unsigned)cur * (unsigned)RRTB_MOTION_NODE_F4;
+        float4 ax, ay, az, bx, by, bz, g0, g1, g2, rr;
+        ldg256(q, ax, ay);     // c0.x[4] c0.y[4]
+        ldg256(q + 2, az, bx); // c0.z[4] c1.x[4]
+        ldg256(q + 4, by, bz); // c1.y[4] c1.z[4]
+        ldg256(q + 6, g0, g1); // bf16 pairs h0.x(0,1) h0.x(2,3) h0.y(0,1) h0.y(2,3) | h0.z(0,1) h0.z(2,3) h1.x(0,1) h1.x(2,3)
+        ldg256(q + 8, g2, rr); // bf16 pairs h1.y(0,1) h1.y(2,3) h1.z(0,1) h1.z(2,3) | refs
+        rf = make_int4(__float_as_int(rr.x), __float_as_int(rr.y), __float_as_int(rr.z), __float_as_int(rr.w));
+        const float s = p.s, oms = 1.0f - p.s;
+        box_hit_pair(lerp2(pack2(ax.x, ax.y), pack2(bx.x, bx.y), s, oms), lerp2(pack2(ay.x, ay.y), pack2(by.x, by.y), s, oms),
+                     lerp2(pack2(az.x, az.y), pack2(bz.x, bz.y), s, oms), lerp2(bf16x2(g0.x), bf16x2(g1.z), s, oms),
+                     lerp2(bf16x2(g0.z), bf16x2(g2.x), s, oms), lerp2(bf16x2(g1.x), bf16x2(g2.z), s, oms), p, t_min, t_max, h0, h1, t0, t1);
+        box_hit_pair(lerp2(pack2(ax.z, ax.w), pack2(bx.z, bx.w), s, oms), lerp2(pack2(ay.z, ay.w), pack2(by.z, by.w), s, oms),
+                     lerp2(pack2(az.z, az.w), pack2(bz.z, bz.w), s, oms), lerp2(bf16x2(g0.y), bf16x2(g1.w), s, oms),
+                     lerp2(bf16x2(g0.w), bf16x2(g2.y), s, oms), lerp2(bf16x2(g1.y), bf16x2(g2.w), s, oms), p, t_min, t_max, h2, h3, t2, t3);
+    }
+    else {
+        // the index is widened before it is scaled so that the address is ONE IMAD.WIDE (cur * 96 + base)
+        const float4 *q = wnodes + (size_t)(unsigned)cur * (unsigned)RRTB_NODE_F4;
+        float4 cx, cy, cz, hw, zr, rs;
+        ldg256(q, cx, cy);     // c.x[4] c.y[4]
+        ldg256(q + 2, cz, hw); // c.z[4], bf16 pairs h.x(0,1) h.x(2,3) h.y(0,1) h.y(2,3)
+        ldg256(q + 4, zr, rs); // bf16 pairs h.z(0,1) h.z(2,3), ref[0..1] | ref[2..3], unused
+        rf = make_int4(__float_as_int(zr.z), __float_as_int(zr.w), __float_as_int(rs.x), __float_as_int(rs.y));
+        box_hit_pair(pack2(cx.x, cx.y), pack2(cy.x, cy.y), pack2(cz.x, cz.y), bf16x2(hw.x), bf16x2(hw.z), bf16x2(zr.x), p, t_min, t_max,
+                     h0, h1, t0, t1);
+        box_hit_pair(pack2(cx.z, cx.w), pack2(cy.z, cy.w), pack2(cz.z, cz.w), bf16x2(hw.y), bf16x2(hw.w), bf16x2(zr.y), p, t_min, t_max,
+                     h2, h3, t2, t3);
+    }
     const int k0 = h0 ? (__float_as_int(t0) & ~3) : KEY_MISS;
     const int k1 = h1 ? ((__float_as_int(t1) & ~3) | 1) : KEY_MISS;
     const int k2 = h2 ? ((__float_as_int(t2) & ~3) | 2) : KEY_MISS;
@@ -585,6 +624,15 @@ __device__ __forceinline__ Hit closest_bvh(const DeviceScene &s, const Ray &r, c
     int stack[RRTB_STACK];
     int sp = 0;
     int cur = 0;
+    if (s.motion) { // interpolating nodes: where the ray's time lies in the shutter
+        RayPre pm = p;
+        pm.s = (r.tm - s.shutter_open) * s.shutter_inv;
+        while (cur != TRAV_DONE) {
+            if (cur >= 0) wide_step<COUNT, true>(s.wnodes, pm, t_min, best.t, cur, sp, stack, cnt);
+            else leaf_step<COUNT>(s.leaves, LeafAux{s.leaf_info, s.leaf_ext}, r, p, t_min, best, cur, sp, stack, cnt);
+        }
+        return best;
+    }
     while (cur != TRAV_DONE) {
         if (cur >= 0) wide_step<COUNT>(s.wnodes, p, t_min, best.t, cur, sp, stack, cnt);
         else leaf_step<COUNT>(s.leaves, LeafAux{s.leaf_info, s.leaf_ext}, r, p, t_min, best, cur, sp, stack, cnt);

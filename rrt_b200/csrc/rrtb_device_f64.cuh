@@ -235,9 +235,12 @@ __device__ __forceinline__ HitD closest_bvh_d(const DeviceScene &s, const RayD &
     int stack[RRTB_STACK];
     int sp = 0;
     int cur = 0;
+    RayPre pm = p;
+    if (s.motion) pm.s = (__double2float_rn(r.tm) - s.shutter_open) * s.shutter_inv;
     while (cur != TRAV_DONE) {
         if (cur >= 0) {
-            wide_step<COUNT>(s.wnodes, p, t_min_f, __double2float_ru(best.t), cur, sp, stack, cnt);
+            if (s.motion) wide_step<COUNT, true>(s.wnodes, pm, t_min_f, __double2float_ru(best.t), cur, sp, stack, cnt);
+            else wide_step<COUNT>(s.wnodes, p, t_min_f, __double2float_ru(best.t), cur, sp, stack, cnt);
         }
         else {
             leaf_test_d<COUNT>(s.leaves, LeafAux{s.leaf_info, s.leaf_ext}, (~cur) >> 2, (~cur) & 3, r, t_min, best, cnt);

@@ -38,6 +38,11 @@ struct rrtb_ctx {
     int *d_left = nullptr, *d_right = nullptr; // [n-1]
     int *d_parent = nullptr;        // [2n-1]
     float *d_node_box = nullptr;    // [6(n-1)]
+    // scenes with motion (moving primitives and an open shutter): boxes at the two ends of the shutter, for the
+    // interpolating traversal nodes (rrtb_device.cuh "Motion node")
+    bool motion = false;
+    float *d_prim_box01 = nullptr;  // [12n]
+    float *d_node_box01 = nullptr;  // [12(n-1)]
     int *d_visit = nullptr;         // [n-1]
     // device: traversal structures
     float4 *d_wnodes = nullptr;     // [8*max(n-1,1)] 4-wide traversal nodes (rrtb_bvh.cu k_collapse4)

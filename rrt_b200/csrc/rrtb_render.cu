@@ -360,6 +360,9 @@ DeviceScene device_scene(const rrtb_ctx *ctx)
 {
     DeviceScene s;
     s.wnodes = ctx->d_wnodes;
+    s.motion = ctx->motion ? 1 : 0;
+    s.shutter_open = ctx->cam.time0;
+    s.shutter_inv = ctx->motion ? 1.0f / (ctx->cam.time1 - ctx->cam.time0) : 0.f;
     s.leaves = ctx->d_leaves;
     s.leaf_info = ctx->d_leaf_info;
     s.flat_leaves = ctx->d_prim;
@@ -495,8 +498,13 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
     if (a.n_items > 0 && a.max_depth > 0) { // max_depth 0: the bounce loop never runs (rrt.cu:47), the image is black
         const bool bvh = ctx->use_bvh != 0, cnt = p->count_rays != 0;
         int rc;
+        const bool mo = ctx->motion; // moving primitives under an open shutter: the kernels walk interpolating motion nodes
         if (f64 && use_pool) { // the pool scheduler over the double path policy
-            if (cnt) rc = launch_pool<PathF64>(ctx, k_render_pool<true, NODE_UNROLL, true, PathF64>, a, &blocks);
+            if (mo) {
+                if (cnt) rc = launch_pool<PathF64>(ctx, k_render_pool<true, NODE_UNROLL, true, PathF64, true>, a, &blocks);
+                else rc = launch_pool<PathF64>(ctx, k_render_pool<false, NODE_UNROLL, true, PathF64, true>, a, &blocks);
+            }
+            else if (cnt) rc = launch_pool<PathF64>(ctx, k_render_pool<true, NODE_UNROLL, true, PathF64>, a, &blocks);
             else rc = launch_pool<PathF64>(ctx, k_render_pool<false, NODE_UNROLL, true, PathF64>, a, &blocks);
         }
         else if (f64) {
@@ -506,7 +514,14 @@ int launch_render(rrtb_ctx *ctx, const rrtb_render_params *p, uint64_t *d_accum,
             else rc = launch_persistent(ctx, k_render_f64<false, false>, a, &blocks);
         }
         else if (use_pool) {
-            if (ctx->n_mtriangles > 0) { // scenes with moving triangles get the variant that knows them
+            const bool mt = ctx->n_mtriangles > 0; // scenes with moving triangles get the variant that knows them
+            if (mo) { // (moving spheres only: MTRI = false)
+                if (mt && cnt) rc = launch_pool<PathF32>(ctx, k_render_pool<true, NODE_UNROLL, true, PathF32, true>, a, &blocks);
+                else if (mt) rc = launch_pool<PathF32>(ctx, k_render_pool<false, NODE_UNROLL, true, PathF32, true>, a, &blocks);
+                else if (cnt) rc = launch_pool<PathF32>(ctx, k_render_pool<true, NODE_UNROLL, false, PathF32, true>, a, &blocks);
+                else rc = launch_pool<PathF32>(ctx, k_render_pool<false, NODE_UNROLL, false, PathF32, true>, a, &blocks);
+            }
+            else if (mt) {
                 if (cnt) rc = launch_pool<PathF32>(ctx, k_render_pool<true, NODE_UNROLL, true>, a, &blocks);
                 else rc = launch_pool<PathF32>(ctx, k_render_pool<false, NODE_UNROLL, true>, a, &blocks);
             }

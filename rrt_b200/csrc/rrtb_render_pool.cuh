@@ -160,7 +160,7 @@ struct PathF64 { // the double integrator (rrtb_device_f64.cuh); bit-exact again
     }
 };
 
-template <bool COUNT_RAYS, int NODE_UNROLL, bool MTRI = false, class P = PathF32>
+template <bool COUNT_RAYS, int NODE_UNROLL, bool MTRI = false, class P = PathF32, bool MOTION = false>
 __global__ void __launch_bounds__(RENDER_TPB, P::BLOCKS_PER_SM) k_render_pool(const RenderArgs a)
 {
     typedef typename P::real real;
@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(RENDER_TPB, P::BLOCKS_PER_SM) k_render_pool(co
                 ray.dx = wp.dx[slot]; ray.dy = wp.dy[slot]; ray.dz = wp.dz[slot];
                 ray.tm = wp.tm[slot];
                 pre = P::pre(ray);
+                if (MOTION) pre.s = ((float)ray.tm - s.shutter_open) * s.shutter_inv; // where the ray's time lies in the shutter
                 best.t = P::inf();
                 best.ref = -1;
                 cur = 0;
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(RENDER_TPB, P::BLOCKS_PER_SM) k_render_pool(co
             do {
 #pragma unroll
                 for (int u = 0; u < NODE_UNROLL; ++u) // node visits between two continue-votes
-                    if (cur >= 0) wide_step<COUNT_RAYS>(wnodes, pre, P::t_min_f(), P::t_max_f(best), cur, sp, stack, tc);
+                    if (cur >= 0) wide_step<COUNT_RAYS, MOTION>(wnodes, pre, P::t_min_f(), P::t_max_f(best), cur, sp, stack, tc);
             } while (++it < a.step_iters && __popc(__ballot_sync(0xffffffffu, cur >= 0)) >= a.th_node);
             const bool at_leaf = cur < 0 && cur != TRAV_DONE;
             const unsigned leaf_mask = __ballot_sync(0xffffffffu, at_leaf);

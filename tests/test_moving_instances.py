@@ -412,3 +412,76 @@ def test_gpu_keyframed_blur_is_the_time_average(ctx, tmp_path):
     b = np.sqrt(acc / n_t).clip(0, 1)
     assert abs(a.mean() - b.mean()) < 4e-3
     assert np.abs(a - b).mean() < 0.03
+
+
+def fast_spheres_scene(n=64, travel=3.0, seed=7, shutter=(0.0, 1.0)):
+    """n small spheres that each travel `travel` units (30 radii) during the shutter, over a ground sphere."""
+    from oracle_lib import camera_derive
+    from rrt_b200.types import SceneArrays, material_dtype, msphere_dtype, sphere_dtype
+
+    rng = np.random.default_rng(seed)
+    mats = np.zeros(3, material_dtype)
+    mats["type"] = [0, 1, 2]
+    mats["albedo"][0] = (0.6, 0.5, 0.4)
+    mats["albedo"][1] = (0.8, 0.8, 0.9)
+    mats["param"] = [0, 0.1, 1.5]
+    ms = np.zeros(n, msphere_dtype)
+    c0 = rng.uniform(-4, 4, size=(n, 3)).astype(np.float32)
+    c0[:, 1] = rng.uniform(0.2, 2.5, size=n)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True) * travel).astype(np.float32)
+    ms["center0"], ms["center1"] = c0, c0 + d
+    ms["time0"], ms["time1"] = 0.0, 1.0
+    ms["radius"] = 0.1
+    ms["material"] = rng.integers(0, 3, size=n)
+    sp = np.zeros(1, sphere_dtype)
+    sp[0] = ((0, -1000, 0), 1000.0, 0)
+    cam = camera_derive((0, 3, 12), (0, 1, 0), (0, 1, 0), 40.0, 1.6, 0.0, 12.0, *shutter)
+    return SceneArrays(cam, mats, sp, ms)
+
+
+@pytest.mark.gpu
+def test_gpu_motion_nodes_interpolate_their_boxes(ctx):
+    """Moving primitives under an open shutter are traversed through MOTION nodes whose child boxes are interpolated at
+    the ray's time (rrtb_device.cuh "Motion node").  (1) Conservative: closest hits (ids, t, records) equal the flat
+    scan and the oracle bit for bit at random times of the shutter, both integrators; whole f64 framebuffers equal the
+    oracle's.  (2) Tight: far fewer exact sphere tests per ray than the oracle's traversal of boxes that span the
+    whole shutter (the reference's moving_sphere::bounding_box)."""
+    from test_gpu_edge_cases import check_wide_tree
+
+    sc = fast_spheres_scene()
+    orc = Oracle(sc)
+    ctx.set_scene(sc, use_bvh=True)
+    check_wide_tree(ctx, sc.n_objects)  # downloaded as the union of the two end boxes: encloses the canonical boxes
+    W, H = 200, 125
+    rays = pinhole_rays(sc, W, H)
+    rays[:, 6] = np.random.default_rng(1).uniform(0, 1, len(rays)).astype(np.float32)
+    want = orc.trace(rays, 0.001, "bvh", want_rec=True)
+    for mode in ("scan", "bvh"):
+        for x, y in zip(ctx.trace(rays, 0.001, mode, want_rec=True), want):
+            assert x.tobytes() == y.tobytes(), mode
+    want64 = orc.trace_f64(rays.astype(np.float64), 0.001, "bvh", want_rec=True)
+    for x, y in zip(ctx.trace_f64(rays.astype(np.float64), 0.001, "bvh", want_rec=True), want64):
+        assert x.tobytes() == y.tobytes()
+    assert (want[0] >= 1).sum() > 150  # moving spheres are hit
+    w, h, spp = 96, 60, 8
+    ref64, _, oc = orc.render_f64(w, h, spp, 50, 5)
+    img64, st64 = ctx.render(w, h, spp, 50, seed=5, count_rays=True, dtype=np.float64, precision="f64")
+    assert img64.tobytes() == ref64.tobytes() and st64["rays"] == oc["rays"]
+    f1, s1 = ctx.render(w, h, spp, 50, seed=5, scheduler=1, count_rays=True)
+    f2, s2 = ctx.render(w, h, spp, 50, seed=5, scheduler=2, count_rays=True)
+    assert f1.tobytes() == f2.tobytes() and s1["rays"] == s2["rays"]
+    ctx.set_scene(sc, use_bvh=False)
+    f3, _ = ctx.render(w, h, spp, 50, seed=5)
+    assert f3.tobytes() == f1.tobytes()
+    # tightness: exact moving-sphere tests per ray, motion nodes vs the oracle's shutter-spanning boxes
+    _, _, ocf = orc.render(w, h, spp, 50, 5)
+    ours, theirs = s2["msphere_tests"] / s2["rays"], ocf["msphere_tests"] / ocf["rays"]
+    assert ours < 0.5 * theirs, (ours, theirs)
+    # a closed shutter has no motion: plain nodes, same answers as the oracle
+    frozen = fast_spheres_scene(shutter=(0.4, 0.4))
+    ctx.set_scene(frozen, use_bvh=True)
+    r2 = pinhole_rays(frozen, W, H)
+    r2[:, 6] = 0.4
+    for x, y in zip(ctx.trace(r2, 0.001, "bvh", want_rec=True), Oracle(frozen).trace(r2, 0.001, "bvh", want_rec=True)):
+        assert x.tobytes() == y.tobytes()
