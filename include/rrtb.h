@@ -121,7 +121,11 @@ int rrtb_device_info(rrtb_ctx *ctx, int64_t *out4, char *name, int name_len);
  * insertion order: spheres, moving spheres, triangles (rrt.cu:151-164).  With use_bvh != 0 a
  * GPU LBVH (30-bit Morton codes, radix sort, Karras hierarchy, bottom-up refit) is built on the
  * device; with use_bvh == 0 (`-b`) rays scan the flat primitive list (hittable_list.h:95-117).
- * Moving-sphere boxes span [camera.time0, camera.time1] (rrt.cu:169, moving_sphere.h:60-66). */
+ * Moving-sphere boxes span [camera.time0, camera.time1] (rrt.cu:169, moving_sphere.h:60-66).
+ * One deliberate deviation: sphere boxes use |radius|.  The reference's center -+ radius (sphere.h:60-64) is an
+ * inverted box for the negative radii the book uses for hollow glass, and its bvh can then lose the sphere while
+ * `-b` renders it; here tree and scan agree.  For radius >= 0 the boxes equal the reference's bit for bit.
+ * Every argument is validated before the loaded scene is touched: a rejected call leaves it renderable. */
 int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *materials, int n_materials,
                    const rrtb_sphere *spheres, int n_spheres, const rrtb_msphere *mspheres, int n_mspheres,
                    const rrtb_triangle *triangles, int n_triangles, int use_bvh);

@@ -435,8 +435,10 @@ static void prim_box(const orc_scene *s, int id, float *b)
     if (r.type == 0) {
         const rrtb_sphere *sp = &s->spheres[r.idx];
         for (int k = 0; k < 3; ++k) {
-            b[k] = sp->center[k] - sp->radius;
-            b[3 + k] = sp->center[k] + sp->radius;
+            /* sphere.h:60-64 with |radius|: the reference's center -+ radius is an INVERTED box for the negative radii the
+             * book uses for hollow glass, and its bvh then loses the sphere; equal to the reference for radius >= 0 */
+            b[k] = sp->center[k] - fabsf(sp->radius);
+            b[3 + k] = sp->center[k] + fabsf(sp->radius);
         }
     }
     else if (r.type == 1) {
@@ -448,8 +450,8 @@ static void prim_box(const orc_scene *s, int id, float *b)
             float dc = m->center1[k] - m->center0[k];
             float ca = m->center0[k] + k0 * dc;
             float cb = m->center0[k] + k1 * dc;
-            b[k] = fminf(ca - m->radius, cb - m->radius);
-            b[3 + k] = fmaxf(ca + m->radius, cb + m->radius);
+            b[k] = fminf(ca - fabsf(m->radius), cb - fabsf(m->radius));
+            b[3 + k] = fmaxf(ca + fabsf(m->radius), cb + fabsf(m->radius));
         }
     }
     else if (r.type == 2) {

@@ -883,6 +883,10 @@ int rrtb_scatter(rrtb_ctx *ctx, const float *in16, const uint32_t *rnd4, int n, 
         return RRTB_ERR_NO_SCENE;
     }
     if (n == 0) return RRTB_OK;
+    for (int i = 0; i < n; ++i) { // the kernel indexes the material arrays with in16[14]
+        const float m = in16[16 * (size_t)i + 14];
+        if (!(m >= 0.0f && m < (float)ctx->n_materials)) return invalid(ctx, "scatter: material index out of range");
+    }
     RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
     DevBuf di, dr, dout;
     HOOK_ALLOC(di, 64 * (size_t)n);
@@ -953,6 +957,10 @@ int rrtb_scatter_f64(rrtb_ctx *ctx, const double *in16, const uint32_t *rnd4, in
         return RRTB_ERR_NO_SCENE;
     }
     if (n == 0) return RRTB_OK;
+    for (int i = 0; i < n; ++i) {
+        const double m = in16[16 * (size_t)i + 14];
+        if (!(m >= 0.0 && m < (double)ctx->n_materials)) return invalid(ctx, "scatter: material index out of range");
+    }
     RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
     DevBuf di, dr, dout;
     HOOK_ALLOC(di, 128 * (size_t)n);

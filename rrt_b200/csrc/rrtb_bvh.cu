@@ -75,9 +75,13 @@ __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__
             rrtb_sphere s = sph[id];
             a = make_float4(s.center[0], s.center[1], s.center[2], s.radius);
             mat = s.material;
+            // sphere.h:60-64 with |radius|: the reference's center -+ radius is an INVERTED box for the negative radii the
+            // book uses for hollow glass (its bvh then loses the sphere while the flat scan renders it); for radius >= 0
+            // this is the reference's box bit for bit
+            const float ar = fabsf(s.radius);
             for (int k = 0; k < 3; ++k) {
-                mn[k] = __fsub_rn(s.center[k], s.radius);
-                mx[k] = __fadd_rn(s.center[k], s.radius);
+                mn[k] = __fsub_rn(s.center[k], ar);
+                mx[k] = __fadd_rn(s.center[k], ar);
             }
         }
         else if (id < ns + nms) {
@@ -86,16 +90,17 @@ __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__
             float k0 = __fdiv_rn(__fsub_rn(cam_t0, m.time0), dt);
             float k1 = __fdiv_rn(__fsub_rn(cam_t1, m.time0), dt);
             float dc[3];
+            const float ar = fabsf(m.radius);
             for (int k = 0; k < 3; ++k) {
                 dc[k] = __fsub_rn(m.center1[k], m.center0[k]);
                 float ca = __fadd_rn(m.center0[k], __fmul_rn(k0, dc[k]));
                 float cb = __fadd_rn(m.center0[k], __fmul_rn(k1, dc[k]));
-                mn[k] = fminf(__fsub_rn(ca, m.radius), __fsub_rn(cb, m.radius));
-                mx[k] = fmaxf(__fadd_rn(ca, m.radius), __fadd_rn(cb, m.radius));
-                e0[k] = __fsub_rn(ca, m.radius);
-                e0[3 + k] = __fadd_rn(ca, m.radius);
-                e1x[k] = __fsub_rn(cb, m.radius);
-                e1x[3 + k] = __fadd_rn(cb, m.radius);
+                mn[k] = fminf(__fsub_rn(ca, ar), __fsub_rn(cb, ar));
+                mx[k] = fmaxf(__fadd_rn(ca, ar), __fadd_rn(cb, ar));
+                e0[k] = __fsub_rn(ca, ar);
+                e0[3 + k] = __fadd_rn(ca, ar);
+                e1x[k] = __fsub_rn(cb, ar);
+                e1x[3 + k] = __fadd_rn(cb, ar);
             }
             moving = true;
             a = make_float4(m.center0[0], m.center0[1], m.center0[2], m.radius);

@@ -312,3 +312,40 @@ print("violations", worst)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, RRTB_LIB=dbg))
     assert r.returncode == 0, r.stderr[-800:]
     assert "violations 0" in r.stdout, r.stdout
+
+
+def test_negative_radius_sphere_keeps_its_box(ctx):
+    """The book's hollow-glass trick (a sphere of NEGATIVE radius inside a glass sphere): the reference's bounding_box is
+    center -+ radius, an inverted box, and its bvh can lose the sphere while the flat scan renders it.  Boxes here use
+    |radius|: tree traversal == flat scan == oracle, and the bubble is really hit."""
+    scene = make_scene(spheres=[((0, 0.6, 0), 0.6, 2), ((0, 0.6, 0), -0.5, 2), ((1.5, 0.4, 0.3), 0.4, 0), ((-1.4, 0.3, 0.5), -0.3, 1),
+                                ((0, -100.5, 0), 100.0, 0)])
+    ctx.set_scene(scene, use_bvh=True)
+    check_wide_tree(ctx, 5)
+    box = ctx.bvh_arrays()["prim_box"]
+    assert np.all(box[:, :3] <= box[:, 3:])
+    rays = random_rays(4000, seed=3)
+    i_b, t_b, r_b = ctx.trace(rays, 0.001, "bvh", want_rec=True)
+    i_s, t_s, r_s = ctx.trace(rays, 0.001, "scan", want_rec=True)
+    assert np.array_equal(i_b, i_s) and t_b.tobytes() == t_s.tobytes() and r_b.tobytes() == r_s.tobytes()
+    o = Oracle(scene)
+    i_o, t_o = o.trace(rays, 0.001, "bvh")
+    assert np.array_equal(i_b, i_o) and t_b.tobytes() == t_o.tobytes()
+    assert (i_b == 1).sum() > 0 or (i_b == 3).sum() > 0
+    a, _ = ctx.render(64, 40, 4, 50, seed=2)
+    ctx.set_scene(scene, use_bvh=False)
+    b, _ = ctx.render(64, 40, 4, 50, seed=2)
+    assert a.tobytes() == b.tobytes()
+
+
+def test_scatter_hook_rejects_bad_material_index(ctx):
+    from rrt_b200 import RrtbError
+
+    scene = make_scene(spheres=[((0, 0.5, 0), 1.0, 0)])
+    ctx.set_scene(scene)
+    in16 = np.zeros((2, 16), np.float32)
+    in16[:, 3:6] = (0, 0, -1)
+    in16[:, 10:13] = (0, 0, 1)
+    in16[1, 14] = 99
+    with pytest.raises(RrtbError):
+        ctx.scatter(in16, np.zeros((2, 4), np.uint32))
