@@ -161,6 +161,18 @@ int rrtb_device_info(rrtb_ctx *ctx, int64_t *out4, char *name, int name_len)
     return RRTB_OK;
 }
 
+// the collapse kernel's work list drained (CollapseState::stuck == 0)?  Read after the build has been synchronised.
+static int check_collapse(rrtb_ctx *ctx)
+{
+    int state[4] = {0, 0, 0, 0};
+    RRTB_CUDA(ctx, cudaMemcpy(state, ctx->d_collapse, sizeof(state), cudaMemcpyDeviceToHost));
+    if (state[3]) {
+        ctx->err = "internal error: the 4-wide collapse did not terminate (inconsistent tree)";
+        return RRTB_ERR_CUDA;
+    }
+    return RRTB_OK;
+}
+
 int rrtb_scene_stage_moving_triangles(rrtb_ctx *ctx, const rrtb_mtriangle *mtriangles, int n_mtriangles)
 {
     if (!ctx || n_mtriangles < 0 || (n_mtriangles > 0 && !mtriangles)) return RRTB_ERR_INVALID;
@@ -234,13 +246,19 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     if ((rc = dev_reserve(ctx, ctx->d_parent, (size_t)2 * n))) return rc;
     if ((rc = dev_reserve(ctx, ctx->d_node_box, (size_t)6 * n))) return rc;
     if ((rc = dev_reserve(ctx, ctx->d_visit, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_range, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_left2, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_right2, (size_t)n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_parent2, (size_t)2 * n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_node_box2, (size_t)6 * n))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_sah_roots, (size_t)n))) return rc;
     if ((rc = dev_reserve(ctx, ctx->d_wnodes, (size_t)(n_mspheres + n_mtriangles > 0 ? RRTB_MOTION_NODE_F4 : RRTB_NODE_F4) * n))) return rc;
     if (n_mspheres + n_mtriangles > 0) { // room for the end-of-shutter boxes whatever this camera's shutter is (rrtb_camera_set may open it)
         if ((rc = dev_reserve(ctx, ctx->d_prim_box01, (size_t)12 * n))) return rc;
         if ((rc = dev_reserve(ctx, ctx->d_node_box01, (size_t)12 * n))) return rc;
     }
     if ((rc = dev_reserve(ctx, ctx->d_wq, (size_t)n))) return rc;
-    if ((rc = dev_reserve(ctx, ctx->d_collapse, (size_t)4))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_collapse, (size_t)16))) return rc; // CollapseState, SahState
     if ((rc = dev_reserve(ctx, ctx->d_leaves, (size_t)3 * n))) return rc;
     if ((rc = dev_reserve(ctx, ctx->d_leaf_info, (size_t)n))) return rc;
     if (n_mtriangles > 0) { // edge rates of moving triangles: two float4 per slot, only for scenes that have them
@@ -288,6 +306,7 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     float ms = 0.f;
     RRTB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->seconds_build = ms * 1e-3;
+    if ((rc = check_collapse(ctx))) return rc;
     ctx->has_scene = true;
     return RRTB_OK;
 }
@@ -320,6 +339,7 @@ int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam)
         float ms = 0.f;
         RRTB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->seconds_build = ms * 1e-3;
+        if ((rc = check_collapse(ctx))) return rc;
         ctx->has_scene = true;
     }
     return RRTB_OK;

@@ -514,8 +514,9 @@ __device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, 
 // entry distance already exceeds the closest hit is skipped at pop time (-12 % leaf tests, but twice the local-memory
 // traffic: 5 % slower), a full sort of the hit children (more instructions than the visits it saves), and the
 // binary tree itself (two children per node: 3 % slower on the headline scene, 10 % on the 1.1 M-primitive one).
-// A collapsed tree is never deeper than the binary tree it comes from (<= 62 levels for 30-bit Morton codes with
-// an index tie-break) and a visit pushes at most three entries, so 192 entries can not overflow; the entries
+// A collapsed tree is never deeper than the binary tree it comes from: <= 62 levels for the Karras tree (30-bit
+// Morton codes with an index tie-break), and the SAH rebuild of its lower subtrees (rrtb_bvh.cu k_sah_rebuild) keeps
+// every leaf within 63 levels; a visit pushes at most three entries, so 192 entries can not overflow.  The entries
 // live in local memory (L1-resident).
 #define RRTB_WIDTH 4
 #define RRTB_NODE_F4 6 // float4 per traversal node (96 B)

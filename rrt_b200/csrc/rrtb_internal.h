@@ -44,6 +44,12 @@ struct rrtb_ctx {
     float *d_prim_box01 = nullptr;  // [12n]
     float *d_node_box01 = nullptr;  // [12(n-1)]
     int *d_visit = nullptr;         // [n-1]
+    // SAH-rebuilt copy of the topology, for the traversal tree only (rrtb_bvh.cu k_sah_rebuild)
+    int2 *d_range = nullptr;        // [n-1] sorted positions covered by each canonical internal node
+    int *d_left2 = nullptr, *d_right2 = nullptr; // [n-1]
+    int *d_parent2 = nullptr;       // [2n-1]
+    float *d_node_box2 = nullptr;   // [6(n-1)]
+    int *d_sah_roots = nullptr;     // [n] roots of the subtrees to rebuild
     // device: traversal structures
     float4 *d_wnodes = nullptr;     // [8*max(n-1,1)] 4-wide traversal nodes (rrtb_bvh.cu k_collapse4)
     int *d_wq = nullptr;            // [n] collapse work list: binary node that roots wide node i

@@ -114,7 +114,7 @@ def test_gpu_config5_full_size(ctx, tmp_path):
         assert np.array_equal(got[k], want[k]), k
     assert got["node_box"].tobytes() == want["node_box"].tobytes()
     m, wd = check_wide_tree(ctx, 1_103_524)
-    assert wd == 4 and m < 1_103_524 // 2
+    assert wd == 4 and m < 0.56 * 1_103_524  # ~0.5 wide nodes per primitive (the SAH-rebuilt subtrees fill their slots to 75 %)
     rays = pinhole_rays(scene.arrays, W, H, step=8)  # 480 x 270 pixel centres of the 4K image
     i_b, t_b = ctx.trace(rays, 0.001, "bvh")
     o_i, o_t = orc.trace(rays, 0.001, "bvh")

@@ -26,7 +26,7 @@ class LabCounters(C.Structure):
 def lab():
     so = os.path.join(ROOT, "tools", "treelab", "libtreelab.so")
     lib = C.CDLL(so)
-    for f in ("lab_build_sah", "lab_from_arrays", "lab_collapse", "lab_build_ploc"):
+    for f in ("lab_build_sah", "lab_from_arrays", "lab_collapse", "lab_build_ploc", "lab_build_hybrid"):
         getattr(lib, f).restype = C.c_void_p
     lib.lab_sah_cost.restype = C.c_double
     lib.lab_sah_cost.argtypes = [C.c_void_p]
@@ -89,6 +89,11 @@ def run(scene, rays, label=""):
     trees = {}
     trees["lbvh"] = C.c_void_p(L.lab_from_arrays(n, vp(pbox), vp(ba["left"]), vp(ba["right"]), vp(ba["perm"])))
     trees["sah"] = C.c_void_p(L.lab_build_sah(n, vp(pbox)))
+    for bins in (8, 16, 32):
+        L.lab_set_sah(0, bins)
+        trees["hyb512b%d" % bins] = C.c_void_p(L.lab_build_hybrid(trees["lbvh"], 512))
+    L.lab_set_sah(4096, 32)
+    trees["hyb512sweep"] = C.c_void_p(L.lab_build_hybrid(trees["lbvh"], 512))
     for r in ():
         trees["ploc%d" % r] = C.c_void_p(L.lab_build_ploc(n, vp(pbox), vp(ba["perm"]), r))
     for name, t in trees.items():
@@ -102,7 +107,7 @@ def run(scene, rays, label=""):
                 w = C.c_void_p(L.lab_collapse(t, k))
                 L.lab_quantise(w, q)
                 L.lab_axis_sort(w)
-                for cull, om in ((0, 0), (0, 1), (0, 2)):
+                for cull, om in ((0, 1),):
                     L.lab_set_order(om)
                     c = LabCounters()
                     L.lab_trace_wide(w, C.byref(o._s), vp(rays), m, C.c_float(0.001), cull, C.byref(c), vp(ids))

@@ -21,11 +21,13 @@ static box_t refit(btree *t, int c){ if(c<0) return t->pbox[~c]; box_t a=refit(t
 /* ---- SAH builder (full sweep for small ranges, binned for large) ---- */
 static const box_t *g_pb; static int g_axis;
 static int cmp_centroid(const void *a,const void *b){int i=*(const int*)a,j=*(const int*)b;float ci=g_pb[i].lo[g_axis]+g_pb[i].hi[g_axis],cj=g_pb[j].lo[g_axis]+g_pb[j].hi[g_axis];return ci<cj?-1:(ci>cj?1:(i<j?-1:(i>j)));}
+int g_sweep_limit=4096, g_bins=32;
+void lab_set_sah(int sweep_limit,int bins){g_sweep_limit=sweep_limit;g_bins=bins;}
 static int sah_rec(btree *t, int *ids, int n, int *next){
   if(n==1) return ~ids[0];
   int node=(*next)++;
   int best_axis=-1,best_split=-1; double best=INFINITY;
-  if(n<=4096){
+  if(n<=g_sweep_limit){
     double *ra=malloc(sizeof(double)*n);
     for(int ax=0;ax<3;ax++){
       g_axis=ax; g_pb=t->pbox; qsort(ids,n,sizeof(int),cmp_centroid);
@@ -35,14 +37,14 @@ static int sah_rec(btree *t, int *ids, int n, int *next){
     free(ra);
     g_axis=best_axis; g_pb=t->pbox; qsort(ids,n,sizeof(int),cmp_centroid);
   } else {
-    enum{NB=32};
+    enum{NBMAX=64}; const int NB=g_bins;
     box_t cb=box_empty(); for(int i=0;i<n;i++){box_t c; for(int k=0;k<3;k++){c.lo[k]=c.hi[k]=0.5f*(t->pbox[ids[i]].lo[k]+t->pbox[ids[i]].hi[k]);} box_merge(&cb,&c);}
     int bb=-1;
     for(int ax=0;ax<3;ax++){
       float lo=cb.lo[ax],ext=cb.hi[ax]-cb.lo[ax]; if(!(ext>0)) continue;
-      box_t bins[NB]; int cnt[NB]; for(int b=0;b<NB;b++){bins[b]=box_empty();cnt[b]=0;}
+      box_t bins[NBMAX]; int cnt[NBMAX]; for(int b=0;b<NB;b++){bins[b]=box_empty();cnt[b]=0;}
       for(int i=0;i<n;i++){float c=0.5f*(t->pbox[ids[i]].lo[ax]+t->pbox[ids[i]].hi[ax]);int b=(int)((c-lo)/ext*NB);if(b>=NB)b=NB-1;if(b<0)b=0;cnt[b]++;box_merge(&bins[b],&t->pbox[ids[i]]);}
-      double ra[NB]; int rc[NB]; box_t b=box_empty(); int c=0; for(int k=NB-1;k>0;k--){box_merge(&b,&bins[k]);c+=cnt[k];ra[k]=box_area(&b);rc[k]=c;}
+      double ra[NBMAX]; int rc[NBMAX]; box_t b=box_empty(); int c=0; for(int k=NB-1;k>0;k--){box_merge(&b,&bins[k]);c+=cnt[k];ra[k]=box_area(&b);rc[k]=c;}
       b=box_empty(); c=0; for(int k=0;k<NB-1;k++){box_merge(&b,&bins[k]);c+=cnt[k]; if(c==0||rc[k+1]==0)continue; double cost=box_area(&b)*c+ra[k+1]*rc[k+1]; if(cost<best){best=cost;best_axis=ax;bb=k;}}
     }
     if(best_axis<0){ best_split=n/2; }
@@ -71,6 +73,16 @@ btree *lab_build_ploc(int n, const float *pbox6, const uint32_t *perm, int radiu
     memcpy(cl,out,sizeof(int)*k); memcpy(cb,ob,sizeof(box_t)*k); m=k;
   }
   t->root=cl[0]; free(cl);free(nn);free(out);free(cb);free(ob); refit(t,t->root); return t; }
+/* LBVH on top, full SAH below: every maximal LBVH subtree with <= max_leaves leaves is rebuilt by the SAH builder
+ * (what one thread block per subtree would do on the GPU) */
+static int count_leaves(const btree *t,int c){ return c<0?1:count_leaves(t,t->left[c])+count_leaves(t,t->right[c]); }
+static void collect(const btree *t,int c,int *ids,int *n){ if(c<0){ids[(*n)++]=~c;return;} collect(t,t->left[c],ids,n); collect(t,t->right[c],ids,n); }
+static int hybrid_rec(const btree *src,btree *dst,int c,int max_leaves,int *next){
+  if(c<0) return c;
+  int nl=count_leaves(src,c);
+  if(nl<=max_leaves){ int *ids=malloc(sizeof(int)*nl); int k=0; collect(src,c,ids,&k); int r=sah_rec(dst,ids,nl,next); free(ids); return r; }
+  int node=(*next)++; int l=hybrid_rec(src,dst,src->left[c],max_leaves,next); int r=hybrid_rec(src,dst,src->right[c],max_leaves,next); dst->left[node]=l; dst->right[node]=r; return node; }
+btree *lab_build_hybrid(const btree *src,int max_leaves){ btree *t=lab_tree_new(src->n,(const float*)src->pbox); int next=0; t->root=hybrid_rec(src,t,src->root,max_leaves,&next); refit(t,t->root); return t; }
 double lab_sah_cost(const btree *t){ double ra=box_area(&t->box[t->root]),c=0; for(int i=0;i<t->n-1;i++){ c+=box_area(&t->box[i])/ra*2.0; } return c; }
 
 /* ---- ray/box ---- */
