@@ -161,6 +161,12 @@ int rrtb_device_info(rrtb_ctx *ctx, int64_t *out4, char *name, int name_len)
     return RRTB_OK;
 }
 
+// Motion nodes (rrtb_device.cuh) interpolate the child boxes at the ray's time: tighter boxes, but 160-byte nodes and a
+// third more arithmetic per visit.  A handful of moving primitives does not pay for that (scenes/test3.txt, 3 moving
+// spheres: 26.1 Grays/s with motion nodes, 28.5 with shutter-spanning boxes), many do (64 fast spheres: less than half the
+// exact tests per ray), so they are used from 8 moving primitives on, under an open shutter.
+static bool use_motion_nodes(int n_moving, const rrtb_camera *cam) { return n_moving >= 8 && cam->time0 != cam->time1; }
+
 // the collapse kernel's work list drained (CollapseState::stuck == 0)?  Read after the build has been synchronised.
 static int check_collapse(rrtb_ctx *ctx)
 {
@@ -224,7 +230,7 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
     ctx->n_mtriangles = n_mtriangles;
     ctx->n_prims = n;
     ctx->use_bvh = use_bvh ? 1 : 0;
-    ctx->motion = n_mspheres + n_mtriangles > 0 && cam->time0 != cam->time1;
+    ctx->motion = use_motion_nodes(n_mspheres + n_mtriangles, cam);
 
     int rc;
     const int nb = (n + 255) / 256;
@@ -326,7 +332,7 @@ int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam)
     const bool shutter = ctx->n_mspheres + ctx->n_mtriangles > 0 && (cam->time0 != ctx->cam.time0 || cam->time1 != ctx->cam.time1);
     const bool farther = mag > ctx->build_cam_mag;
     ctx->cam = *cam;
-    ctx->motion = ctx->n_mspheres + ctx->n_mtriangles > 0 && cam->time0 != cam->time1;
+    ctx->motion = use_motion_nodes(ctx->n_mspheres + ctx->n_mtriangles, cam);
     if (shutter || farther) {
         RRTB_CUDA(ctx, cudaSetDevice(ctx->device));
         ctx->has_scene = false;

@@ -4,13 +4,13 @@
 # command has exited 0 without ncu).  Numbers printed under ncu are never used as bench values.
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-python bench.py > gpurun_out/r02_bench_final_n1.json 2> gpurun_out/r02_bench_final_n1.err
+timeout 600 python bench.py > gpurun_out/r02_bench_final_n1.json 2> gpurun_out/r02_bench_final_n1.err
 for wl in test2 test3; do
-  python bench.py --workload $wl --steps 5 --warmup 3 --no-baselines 2>/dev/null | tail -1 > gpurun_out/r02_bench_${wl}_n1.json
+  timeout 300 python bench.py --workload $wl --steps 5 --warmup 3 --no-baselines 2>/dev/null | tail -1 > gpurun_out/r02_bench_${wl}_n1.json
 done
-python bench.py --precision f64 --steps 5 --warmup 3 --no-baselines 2>/dev/null | tail -1 > gpurun_out/r02_bench_f64_final.json
-python bench.py --workload final_anim --steps 1 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r02_bench_final_anim.json
-python bench.py --workload synthetic --steps 3 --warmup 3 --no-baselines 2>/dev/null | tail -1 > gpurun_out/r02_bench_synthetic_n1.json
+timeout 300 python bench.py --precision f64 --steps 5 --warmup 3 --no-baselines 2>/dev/null | tail -1 > gpurun_out/r02_bench_f64_final.json
+timeout 300 python bench.py --workload final_anim --steps 1 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r02_bench_final_anim.json
+timeout 600 python bench.py --workload synthetic --steps 3 --warmup 3 --no-baselines 2>/dev/null | tail -1 > gpurun_out/r02_bench_synthetic_n1.json
 # the shipped executable on the headline workload: "took" vs the bench's ms_per_step
 rrt_b200/bin/rrt -i oracle/_ref/scenes/final.txt -w 1200 -h 800 -s 500 -o /tmp/cli.png 2> gpurun_out/r02_cli_final.txt
 rrt_b200/bin/rrt -i oracle/_ref/scenes/final.txt -w 1200 -h 800 -s 500 -R -o /tmp/cli.png 2>> gpurun_out/r02_cli_final.txt
