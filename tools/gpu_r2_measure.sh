@@ -12,20 +12,21 @@ timeout 300 python bench.py --precision f64 --steps 5 --warmup 3 --no-baselines 
 timeout 300 python bench.py --workload final_anim --steps 1 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r02_bench_final_anim.json
 timeout 600 python bench.py --workload synthetic --steps 3 --warmup 3 --no-baselines 2>/dev/null | tail -1 > gpurun_out/r02_bench_synthetic_n1.json
 # the shipped executable on the headline workload: "took" vs the bench's ms_per_step
-rrt_b200/bin/rrt -i oracle/_ref/scenes/final.txt -w 1200 -h 800 -s 500 -o /tmp/cli.png 2> gpurun_out/r02_cli_final.txt
-rrt_b200/bin/rrt -i oracle/_ref/scenes/final.txt -w 1200 -h 800 -s 500 -R -o /tmp/cli.png 2>> gpurun_out/r02_cli_final.txt
+timeout 120 rrt_b200/bin/rrt -i oracle/_ref/scenes/final.txt -w 1200 -h 800 -s 500 -o /tmp/cli.png 2> gpurun_out/r02_cli_final.txt
+timeout 120 rrt_b200/bin/rrt -i oracle/_ref/scenes/final.txt -w 1200 -h 800 -s 500 -R -o /tmp/cli.png 2>> gpurun_out/r02_cli_final.txt
 grep -E "took|stats" gpurun_out/r02_cli_final.txt
-python tools/build_time.py > gpurun_out/r02_build_time.log 2>&1
+timeout 120 python tools/cold_warm.py > gpurun_out/r02_cold_warm.txt 2>&1
+timeout 200 python tools/build_time.py > gpurun_out/r02_build_time.log 2>&1
 # ---- ncu
 CMD="python bench.py --steps 2 --warmup 3 --no-baselines"
-$CMD > gpurun_out/r02_plain_launch.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_bench.csv $CMD > gpurun_out/r02_ncu_launch.log 2>&1
-$CMD > gpurun_out/r02_plain_full.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_render_pool -s 4 -c 1 -f -o gpurun_out/r02_final_head $CMD > gpurun_out/r02_ncu_full.log 2>&1
-python tools/run_one.py synthetic 8 > gpurun_out/r02_plain_syn.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_render_pool -s 1 -c 1 -f -o gpurun_out/r02_synth_head python tools/run_one.py synthetic 8 > gpurun_out/r02_ncu_syn.log 2>&1
-python tools/run_one.py final 64 f64 > gpurun_out/r02_plain_f64.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_render_pool -s 1 -c 1 -f -o gpurun_out/r02_f64_head python tools/run_one.py final 64 f64 > gpurun_out/r02_ncu_f64.log 2>&1
+timeout 200 $CMD > gpurun_out/r02_plain_launch.log 2>&1 &&
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_bench.csv $CMD > gpurun_out/r02_ncu_launch.log 2>&1
+timeout 200 $CMD > gpurun_out/r02_plain_full.log 2>&1 &&
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_render_pool -s 4 -c 1 -f -o gpurun_out/r02_final_head $CMD > gpurun_out/r02_ncu_full.log 2>&1
+timeout 200 python tools/run_one.py synthetic 8 > gpurun_out/r02_plain_syn.log 2>&1 &&
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_render_pool -s 1 -c 1 -f -o gpurun_out/r02_synth_head python tools/run_one.py synthetic 8 > gpurun_out/r02_ncu_syn.log 2>&1
+timeout 200 python tools/run_one.py final 64 f64 > gpurun_out/r02_plain_f64.log 2>&1 &&
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_render_pool -s 1 -c 1 -f -o gpurun_out/r02_f64_head python tools/run_one.py final 64 f64 > gpurun_out/r02_ncu_f64.log 2>&1
 ls -la gpurun_out/r02_*
 for f in gpurun_out/r02_bench_*.json; do python - "$f" <<'PY'
 import json,sys

@@ -10,6 +10,7 @@ done
 [ -s $G/r02_launches_bench.csv ] && cp $G/r02_launches_bench.csv $P/r02_launches_bench.csv
 [ -s $G/r02_cli_final.txt ] && grep -E "took|stats" $G/r02_cli_final.txt > $P/r02_cli_final.txt
 [ -s $G/r02_build_time.log ] && cp $G/r02_build_time.log $P/r02_build_time.txt
+[ -s $G/r02_cold_warm.txt ] && cp $G/r02_cold_warm.txt $P/r02_cold_warm.txt
 for k in final synth f64; do
   rep=$G/r02_${k}_head.ncu-rep
   [ -s $rep ] || continue
