@@ -126,6 +126,7 @@ void rrtb_destroy(rrtb_ctx *ctx)
     if (ctx->d_frame) cudaFree(ctx->d_frame);
     if (ctx->d_sum) cudaFree(ctx->d_sum);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_state) cudaFreeHost(ctx->h_state);
     for (cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev2, ctx->ev3, ctx->ev_copy[0], ctx->ev_copy[1]})
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -167,12 +168,19 @@ int rrtb_device_info(rrtb_ctx *ctx, int64_t *out4, char *name, int name_len)
 // exact tests per ray), so they are used from 8 moving primitives on, under an open shutter.
 static bool use_motion_nodes(int n_moving, const rrtb_camera *cam) { return n_moving >= 8 && cam->time0 != cam->time1; }
 
-// the collapse kernel's work list drained (CollapseState::stuck == 0)?  Read after the build has been synchronised.
+// The collapse kernel's work list drained (CollapseState::stuck == 0)?  fetch_collapse_state enqueues the read-back
+// behind the build (pinned destination: it costs no synchronisation of its own), check_collapse reads it after the
+// stream has been synchronised.
+static int fetch_collapse_state(rrtb_ctx *ctx)
+{
+    if (!ctx->h_state) RRTB_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_state, 4 * sizeof(int), cudaHostAllocPortable));
+    RRTB_CUDA(ctx, cudaMemcpyAsync(ctx->h_state, ctx->d_collapse, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return RRTB_OK;
+}
+
 static int check_collapse(rrtb_ctx *ctx)
 {
-    int state[4] = {0, 0, 0, 0};
-    RRTB_CUDA(ctx, cudaMemcpy(state, ctx->d_collapse, sizeof(state), cudaMemcpyDeviceToHost));
-    if (state[3]) {
+    if (ctx->h_state[3]) {
         ctx->err = "internal error: the 4-wide collapse did not terminate (inconsistent tree)";
         return RRTB_ERR_CUDA;
     }
@@ -308,6 +316,7 @@ int rrtb_scene_set(rrtb_ctx *ctx, const rrtb_camera *cam, const rrtb_material *m
         RRTB_CUDA(ctx, cudaMemcpyAsync(d_mtri, mtri.data(), sizeof(rrtb_mtriangle) * (size_t)n_mtriangles, cudaMemcpyHostToDevice, st));
     if ((rc = prepare_and_build(ctx, d_sph, d_msph, d_tri, d_mtri))) return rc;
     RRTB_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    if ((rc = fetch_collapse_state(ctx))) return rc;
     RRTB_CUDA(ctx, cudaStreamSynchronize(st)); // the host arrays (and mats / mtri above) may go away after this
     float ms = 0.f;
     RRTB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -341,6 +350,7 @@ int rrtb_camera_set(rrtb_ctx *ctx, const rrtb_camera *cam)
                                    (const rrtb_triangle *)(ctx->d_stage + ctx->stage_off[2]), (const rrtb_mtriangle *)(ctx->d_stage + ctx->stage_off[3]));
         if (rc) return rc;
         RRTB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        if ((rc = fetch_collapse_state(ctx))) return rc;
         RRTB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         float ms = 0.f;
         RRTB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -826,7 +836,11 @@ int rrtb_bvh_download(rrtb_ctx *ctx, uint32_t *morton, uint32_t *perm, int32_t *
     if (left && ni) RRTB_CUDA(ctx, cudaMemcpy(left, ctx->d_left, 4 * ni, cudaMemcpyDeviceToHost));
     if (right && ni) RRTB_CUDA(ctx, cudaMemcpy(right, ctx->d_right, 4 * ni, cudaMemcpyDeviceToHost));
     if (parent) RRTB_CUDA(ctx, cudaMemcpy(parent, ctx->d_parent, 4 * (2 * n - 1), cudaMemcpyDeviceToHost));
-    if (node_box && ni) RRTB_CUDA(ctx, cudaMemcpy(node_box, ctx->d_node_box, 4 * 6 * ni, cudaMemcpyDeviceToHost));
+    if (node_box && ni) {
+        int rc = refit_canonical(ctx);
+        if (rc) return rc;
+        RRTB_CUDA(ctx, cudaMemcpy(node_box, ctx->d_node_box, 4 * 6 * ni, cudaMemcpyDeviceToHost));
+    }
     if (prim_box) RRTB_CUDA(ctx, cudaMemcpy(prim_box, ctx->d_prim_box, 4 * 6 * n, cudaMemcpyDeviceToHost));
     return RRTB_OK;
 }

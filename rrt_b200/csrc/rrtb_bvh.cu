@@ -410,6 +410,35 @@ __global__ void __launch_bounds__(TPB) k_scatter(const uint64_t *__restrict__ in
     }
 }
 
+// Scenes of at most SMALL_SORT keys (the reference's four scenes have 4 .. 488 primitives) are sorted by ONE block in
+// shared memory: a bitonic network over the whole 64-bit key.  Keys are unique (the id is in the low word), so the
+// result is the order the stable radix passes produce; 20 launches of ~5 us each become one.
+static constexpr int SMALL_SORT = 2048;
+
+__global__ void __launch_bounds__(1024) k_sort_small(uint64_t *__restrict__ keys, int n)
+{
+    __shared__ uint64_t sk[SMALL_SORT];
+    int m = 2;
+    while (m < n) m <<= 1; // padded length
+    for (int i = threadIdx.x; i < m; i += 1024) sk[i] = i < n ? keys[i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (m >> 1); t += 1024) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j; // the t-th pair at distance j
+                const bool up = (lo & k) == 0;
+                const uint64_t a = sk[lo], b = sk[hi];
+                if ((a > b) == up) {
+                    sk[lo] = b;
+                    sk[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += 1024) keys[i] = sk[i];
+}
+
 // ---- Karras 2012 ------------------------------------------------------------------------------------
 __device__ __forceinline__ int delta_fn(const uint64_t *__restrict__ keys, int n, uint64_t ki, int j)
 {
@@ -463,8 +492,7 @@ __global__ void __launch_bounds__(TPB) k_karras(const uint64_t *__restrict__ key
 // other index buffer and emits the two children; runs of one leaf become leaf children at once.
 static constexpr int SAH_MAX = 512;
 static constexpr int SAH_BINS = 32; // one bin per lane: prefix / suffix unions by warp scans (tools/treelab: 8 bins -4.8 %, 16 -6.8 %, 32 -12 % visits on final.txt)
-static constexpr int SAH_TPB = 256;
-static constexpr int SAH_WARPS = SAH_TPB / 32;
+static constexpr int SAH_BIG = 128; // runs longer than this are split by the whole block (blocks of at least SAH_MAX threads only)
 
 struct SahState {
     int n_roots; // subtrees to rebuild
@@ -496,36 +524,140 @@ __device__ __forceinline__ int f2o(float f)
 }
 __device__ __forceinline__ float o2f(int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
 
-__global__ void __launch_bounds__(SAH_TPB) k_sah_rebuild(const uint64_t *__restrict__ keys, int n, const int2 *__restrict__ range,
+// Best split of one task from its bins (lane = bin): the plane after bin `lane` splits the run into bins 0 .. lane and
+// lane + 1 .. 31; their unions by an inclusive prefix scan and an exclusive suffix scan over the lanes.  Returns, in every
+// lane, the cheapest (cost, axis * 32 + bin); cost = +inf when no plane has primitives on both sides.  Lane 31 also gets
+// the box of the whole run (the last inclusive prefix) in `whole`.
+__device__ __forceinline__ void sah_choose(const int (*bn3)[SAH_BINS][7], int lane, float &cost, int &best, float *whole)
+{
+    const float inf = __int_as_float(0x7f800000);
+    cost = inf;
+    best = 0;
+    for (int k = 0; k < 3; ++k) {
+        const int *bn = bn3[k][lane];
+        int pc = bn[0];
+        float plo[3], phi[3];
+        for (int c = 0; c < 3; ++c) {
+            plo[c] = o2f(bn[1 + c]);
+            phi[c] = o2f(bn[4 + c]);
+        }
+        int sc = pc;
+        float slo[3] = {plo[0], plo[1], plo[2]}, shi[3] = {phi[0], phi[1], phi[2]};
+        for (int o = 1; o < 32; o <<= 1) {
+            const int c_up = __shfl_up_sync(0xffffffffu, pc, o), c_dn = __shfl_down_sync(0xffffffffu, sc, o);
+            if (lane >= o) pc += c_up;
+            if (lane + o < 32) sc += c_dn;
+            for (int c = 0; c < 3; ++c) {
+                const float lu = __shfl_up_sync(0xffffffffu, plo[c], o), hu = __shfl_up_sync(0xffffffffu, phi[c], o);
+                const float ld = __shfl_down_sync(0xffffffffu, slo[c], o), hd = __shfl_down_sync(0xffffffffu, shi[c], o);
+                if (lane >= o) {
+                    plo[c] = fminf(plo[c], lu);
+                    phi[c] = fmaxf(phi[c], hu);
+                }
+                if (lane + o < 32) {
+                    slo[c] = fminf(slo[c], ld);
+                    shi[c] = fmaxf(shi[c], hd);
+                }
+            }
+        }
+        if (k == 0)
+            for (int c = 0; c < 3; ++c) {
+                whole[c] = plo[c];
+                whole[3 + c] = phi[c];
+            }
+        // the right side of the plane after bin `lane` is the inclusive suffix of lane + 1
+        const int rc = __shfl_down_sync(0xffffffffu, sc, 1);
+        float rlo[3], rhi[3];
+        for (int c = 0; c < 3; ++c) {
+            rlo[c] = __shfl_down_sync(0xffffffffu, slo[c], 1);
+            rhi[c] = __shfl_down_sync(0xffffffffu, shi[c], 1);
+        }
+        if (lane < 31 && pc > 0 && rc > 0) {
+            const float x0 = phi[0] - plo[0], y0 = phi[1] - plo[1], z0 = phi[2] - plo[2];
+            const float x1 = rhi[0] - rlo[0], y1 = rhi[1] - rlo[1], z1 = rhi[2] - rlo[2];
+            const float ck = (x0 * y0 + y0 * z0 + z0 * x0) * (float)pc + (x1 * y1 + y1 * z1 + z1 * x1) * (float)rc;
+            if (ck < cost) {
+                cost = ck;
+                best = k * 32 + lane;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float oc = __shfl_xor_sync(0xffffffffu, cost, o);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+        if (oc < cost || (oc == cost && ob < best)) {
+            cost = oc;
+            best = ob;
+        }
+    }
+}
+
+__device__ __forceinline__ void sah_bins_clear(int (*bn3)[SAH_BINS][7], int lane)
+{
+    const float inf = __int_as_float(0x7f800000);
+    for (int k = 0; k < 3; ++k) { // lane = bin
+        int *bn = bn3[k][lane];
+        bn[0] = 0;
+        for (int c = 0; c < 3; ++c) {
+            bn[1 + c] = f2o(inf);
+            bn[4 + c] = f2o(-inf);
+        }
+    }
+}
+
+__device__ __forceinline__ void sah_bins_add(int (*bn3)[SAH_BINS][7], const float *box, const float *cmin, const float *scale)
+{
+    for (int k = 0; k < 3; ++k) {
+        const float c = box[k] + box[3 + k];
+        int *bn = bn3[k][min(SAH_BINS - 1, (int)((c - cmin[k]) * scale[k]))];
+        atomicAdd(&bn[0], 1);
+        for (int c3 = 0; c3 < 3; ++c3) {
+            atomicMin(&bn[1 + c3], f2o(box[c3]));
+            atomicMax(&bn[4 + c3], f2o(box[3 + c3]));
+        }
+    }
+}
+
+// One block rebuilds one subtree at a time, level by level.  Per level: tasks of more than SAH_BIG primitives (the top of
+// the subtree: few tasks, long runs) are taken one after the other by the WHOLE block, one primitive per thread; the
+// others by one warp each.  Two shapes: NT = 1024 for scenes of a few subtrees (the reference's scenes are ONE subtree: the
+// build is a latency chain and every level wants all the warps it can get), NT = 256 with four blocks per SM and no
+// block-wide path for large scenes, where there are thousands of subtrees to overlap (1.1 M primitives: 4.0 vs 5.2 ms).
+template <int NT>
+__global__ void __launch_bounds__(NT) k_sah_rebuild(const uint64_t *__restrict__ keys, int n, const int2 *__restrict__ range,
                                                           const float *__restrict__ prim_box, const int *__restrict__ roots,
                                                           const int *__restrict__ parent, SahState *st, int *__restrict__ left2,
-                                                          int *__restrict__ right2, int *__restrict__ parent2)
+                                                          int *__restrict__ right2, int *__restrict__ parent2, float *__restrict__ node_box2)
 {
+    constexpr int SAH_TPB = NT, SAH_WARPS = NT / 32;
+    constexpr bool BLOCK_PATH = NT >= SAH_MAX; // one thread per primitive of a run
+    extern __shared__ int sah_dyn[];
+    int (*bins)[3][SAH_BINS][7] = reinterpret_cast<int (*)[3][SAH_BINS][7]>(sah_dyn); // [SAH_WARPS]: count, min xyz, max xyz (ordered ints)
     __shared__ float sbox[SAH_MAX][6];
     __shared__ unsigned short sidx[2][SAH_MAX];
     __shared__ int q_node[2][SAH_MAX / 2 + 1];
     __shared__ unsigned short q_b[2][SAH_MAX / 2 + 1], q_e[2][SAH_MAX / 2 + 1];
     __shared__ int q_n[2];
     __shared__ int s_alloc, s_root, s_budget;
-    __shared__ int bins[SAH_WARPS][3][SAH_BINS][7]; // count, min xyz, max xyz (ordered ints)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int s_cmin[3], s_cmax[3], s_best, s_median, s_cl[SAH_WARPS], s_cr[SAH_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const int ni = n - 1;
     const float inf = __int_as_float(0x7f800000);
 
     while (true) {
         __syncthreads();
-        if (threadIdx.x == 0) s_root = atomicAdd(&st->ticket, 1);
+        if (tid == 0) s_root = atomicAdd(&st->ticket, 1);
         __syncthreads();
         if (s_root >= st->n_roots) return;
         const int root = roots[s_root];
         const int a = range[root].x, m = range[root].y - range[root].x + 1;
-        for (int l = threadIdx.x; l < m; l += SAH_TPB) {
+        for (int l = tid; l < m; l += SAH_TPB) {
             const int id = (int)(uint32_t)keys[a + l];
             for (int c = 0; c < 6; ++c) sbox[l][c] = prim_box[6 * id + c];
             sidx[0][l] = (unsigned short)l;
         }
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             // The traversal stack (RRTB_STACK = 3 x 64 entries) relies on a tree of at most 63 levels, which the Karras tree
             // guarantees (30-bit codes + 32-bit index tie-break).  The rebuilt subtree gets the levels its root leaves free;
             // a run that could not be finished inside them by halving is split in the middle from there on.
@@ -544,155 +676,229 @@ __global__ void __launch_bounds__(SAH_TPB) k_sah_rebuild(const uint64_t *__restr
         }
         __syncthreads();
         int cur = 0, level = 0;
+        // the two children of `node` over the partitioned run [b, b + nl) [b + nl, e) of sidx[cur ^ 1]: a run of one leaf is a
+        // leaf child, a longer run a new node and a task of the next level (one thread)
+        auto emit = [&](int node, int b, int nl, int e) {
+            int child[2];
+            const int cb[2] = {b, b + nl}, ce[2] = {b + nl, e};
+            for (int sd = 0; sd < 2; ++sd) {
+                if (ce[sd] - cb[sd] == 1) {
+                    const int k = a + sidx[cur ^ 1][cb[sd]];
+                    child[sd] = ~k;
+                    parent2[ni + k] = node;
+                }
+                else {
+                    const int v = atomicAdd(&s_alloc, 1);
+                    child[sd] = v;
+                    parent2[v] = node;
+                    const int q = atomicAdd(&q_n[cur ^ 1], 1);
+                    q_node[cur ^ 1][q] = v;
+                    q_b[cur ^ 1][q] = (unsigned short)cb[sd];
+                    q_e[cur ^ 1][q] = (unsigned short)ce[sd];
+                }
+            }
+            left2[node] = child[0];
+            right2[node] = child[1];
+        };
         while (q_n[cur] > 0) {
             const int n_tasks = q_n[cur];
+            // ---- long runs: the whole block, one primitive per thread (SAH_MAX <= SAH_TPB)
+            for (int t = 0; BLOCK_PATH && t < n_tasks; ++t) {
+                const int node = q_node[cur][t], b = q_b[cur][t], e = q_e[cur][t], cnt = e - b;
+                if (cnt <= SAH_BIG) continue; // block-uniform
+                if (tid < 3) {
+                    s_cmin[tid] = f2o(inf);
+                    s_cmax[tid] = f2o(-inf);
+                }
+                if (warp == 0) sah_bins_clear(bins[0], lane);
+                __syncthreads();
+                const bool valid = tid < cnt;
+                const int l = valid ? sidx[cur][b + tid] : 0;
+                float box[6];
+                for (int c = 0; c < 6; ++c) box[c] = sbox[l][c];
+                if (warp * 32 < cnt) { // centroid bounds (twice the centroid: lo + hi)
+                    for (int k = 0; k < 3; ++k) {
+                        const float c = box[k] + box[3 + k];
+                        const float mn = warp_min(valid ? c : inf), mx = warp_max(valid ? c : -inf);
+                        if (lane == 0) {
+                            atomicMin(&s_cmin[k], f2o(mn));
+                            atomicMax(&s_cmax[k], f2o(mx));
+                        }
+                    }
+                }
+                __syncthreads();
+                float cmin[3], scale[3];
+                for (int k = 0; k < 3; ++k) {
+                    const float cmax = o2f(s_cmax[k]);
+                    cmin[k] = o2f(s_cmin[k]);
+                    scale[k] = cmax > cmin[k] ? (float)SAH_BINS / (cmax - cmin[k]) : 0.f;
+                }
+                if (valid) sah_bins_add(bins[0], box, cmin, scale);
+                __syncthreads();
+                if (warp == 0) {
+                    float cost, whole[6];
+                    int best;
+                    sah_choose(bins[0], lane, cost, best, whole);
+                    if (lane == 31)
+                        for (int c = 0; c < 6; ++c) node_box2[6 * node + c] = whole[c];
+                    if (lane == 0) {
+                        s_best = best;
+                        s_median = !(cost < inf) || level + (32 - __clz(cnt - 1)) >= s_budget;
+                    }
+                }
+                __syncthreads();
+                const int ax = s_best >> 5, sp = s_best & 31;
+                bool go_left = false;
+                if (valid) {
+                    if (s_median) go_left = tid < cnt / 2;
+                    else go_left = min(SAH_BINS - 1, (int)((box[ax] + box[3 + ax] - cmin[ax]) * scale[ax])) <= sp;
+                }
+                const unsigned ml = __ballot_sync(0xffffffffu, go_left), mr = __ballot_sync(0xffffffffu, valid && !go_left);
+                if (lane == 0) {
+                    s_cl[warp] = __popc(ml);
+                    s_cr[warp] = __popc(mr);
+                }
+                __syncthreads();
+                int offl = 0, offr = 0, nl = 0;
+                for (int w = 0; w < SAH_WARPS; ++w) {
+                    if (w < warp) {
+                        offl += s_cl[w];
+                        offr += s_cr[w];
+                    }
+                    nl += s_cl[w];
+                }
+                if (go_left) sidx[cur ^ 1][b + offl + __popc(ml & lt)] = (unsigned short)l;
+                else if (valid) sidx[cur ^ 1][e - 1 - (offr + __popc(mr & lt))] = (unsigned short)l;
+                __syncthreads();
+                if (tid == 0) emit(node, b, nl, e);
+            }
+            // ---- the other runs: one warp each
             for (int t = warp; t < n_tasks; t += SAH_WARPS) {
                 const int node = q_node[cur][t], b = q_b[cur][t], e = q_e[cur][t], cnt = e - b;
-                // centroid bounds (twice the centroid: lo + hi)
-                float cmin[3] = {inf, inf, inf}, cmax[3] = {-inf, -inf, -inf};
-                for (int i = b + lane; i < e; i += 32) {
-                    const int l = sidx[cur][i];
-                    for (int k = 0; k < 3; ++k) {
-                        const float c = sbox[l][k] + sbox[l][3 + k];
-                        cmin[k] = fminf(cmin[k], c);
-                        cmax[k] = fmaxf(cmax[k], c);
-                    }
-                }
-                for (int k = 0; k < 3; ++k) {
-                    cmin[k] = warp_min(cmin[k]);
-                    cmax[k] = warp_max(cmax[k]);
-                }
-                float scale[3];
-                for (int k = 0; k < 3; ++k) scale[k] = cmax[k] > cmin[k] ? (float)SAH_BINS / (cmax[k] - cmin[k]) : 0.f;
-                for (int k = 0; k < 3; ++k) { // lane = bin
-                    int *bn = bins[warp][k][lane];
-                    bn[0] = 0;
-                    for (int c = 0; c < 3; ++c) {
-                        bn[1 + c] = f2o(inf);
-                        bn[4 + c] = f2o(-inf);
-                    }
-                }
-                __syncwarp();
-                for (int i = b + lane; i < e; i += 32) {
-                    const int l = sidx[cur][i];
-                    for (int k = 0; k < 3; ++k) {
-                        const float c = sbox[l][k] + sbox[l][3 + k];
-                        const int bi = min(SAH_BINS - 1, (int)((c - cmin[k]) * scale[k]));
-                        int *bn = bins[warp][k][bi];
-                        atomicAdd(&bn[0], 1);
-                        for (int c3 = 0; c3 < 3; ++c3) {
-                            atomicMin(&bn[1 + c3], f2o(sbox[l][c3]));
-                            atomicMax(&bn[4 + c3], f2o(sbox[l][3 + c3]));
-                        }
-                    }
-                }
-                __syncwarp();
-                // lane = bin: the plane after bin `lane` splits the run into bins 0 .. lane and lane + 1 .. 31; their unions by an
-                // inclusive prefix scan and an exclusive suffix scan over the lanes
-                float cost = inf;
-                int best = 0;
-                for (int k = 0; k < 3; ++k) {
-                    const int *bn = bins[warp][k][lane];
-                    int pc = bn[0];
-                    float plo[3], phi[3];
-                    for (int c = 0; c < 3; ++c) {
-                        plo[c] = o2f(bn[1 + c]);
-                        phi[c] = o2f(bn[4 + c]);
-                    }
-                    int sc = pc;
-                    float slo[3] = {plo[0], plo[1], plo[2]}, shi[3] = {phi[0], phi[1], phi[2]};
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int c_up = __shfl_up_sync(0xffffffffu, pc, o), c_dn = __shfl_down_sync(0xffffffffu, sc, o);
-                        if (lane >= o) pc += c_up;
-                        if (lane + o < 32) sc += c_dn;
+                if (BLOCK_PATH && cnt > SAH_BIG) continue;
+                int nl = 0;
+                if (cnt <= 4) {
+                    // Two to four boxes: EVERY way to split them into two sets (2^(cnt-1) - 1 of them, element 0 on the left), one
+                    // candidate per lane -- exact where the bins are coarsest, and most tasks of a subtree are this small.
+                    float lo4[4][3], hi4[4][3];
+                    for (int i = 0; i < 4; ++i) {
+                        const int l = sidx[cur][b + min(i, cnt - 1)];
                         for (int c = 0; c < 3; ++c) {
-                            const float lu = __shfl_up_sync(0xffffffffu, plo[c], o), hu = __shfl_up_sync(0xffffffffu, phi[c], o);
-                            const float ld = __shfl_down_sync(0xffffffffu, slo[c], o), hd = __shfl_down_sync(0xffffffffu, shi[c], o);
-                            if (lane >= o) {
-                                plo[c] = fminf(plo[c], lu);
-                                phi[c] = fmaxf(phi[c], hu);
+                            lo4[i][c] = sbox[l][c];
+                            hi4[i][c] = sbox[l][3 + c];
+                        }
+                    }
+                    if (lane < 3) { // the node's own box: lanes 0..2 = axes
+                        float lo = lo4[0][lane], hi = hi4[0][lane];
+                        for (int i = 1; i < 4; ++i)
+                            if (i < cnt) {
+                                lo = fminf(lo, lo4[i][lane]);
+                                hi = fmaxf(hi, hi4[i][lane]);
                             }
-                            if (lane + o < 32) {
-                                slo[c] = fminf(slo[c], ld);
-                                shi[c] = fmaxf(shi[c], hd);
+                        node_box2[6 * node + lane] = lo;
+                        node_box2[6 * node + 3 + lane] = hi;
+                    }
+                    const unsigned mask = 1u | ((unsigned)lane << 1);
+                    float cost = inf;
+                    if (lane < (1 << (cnt - 1)) - 1) {
+                        float alo[3] = {inf, inf, inf}, ahi[3] = {-inf, -inf, -inf}, blo[3] = {inf, inf, inf}, bhi[3] = {-inf, -inf, -inf};
+                        for (int i = 0; i < 4; ++i) {
+                            if (i >= cnt) break;
+                            const bool left = (mask >> i) & 1u;
+                            for (int c = 0; c < 3; ++c) {
+                                if (left) {
+                                    alo[c] = fminf(alo[c], lo4[i][c]);
+                                    ahi[c] = fmaxf(ahi[c], hi4[i][c]);
+                                }
+                                else {
+                                    blo[c] = fminf(blo[c], lo4[i][c]);
+                                    bhi[c] = fmaxf(bhi[c], hi4[i][c]);
+                                }
                             }
                         }
+                        const int na = __popc(mask & ((1u << cnt) - 1u));
+                        const float x0 = ahi[0] - alo[0], y0 = ahi[1] - alo[1], z0 = ahi[2] - alo[2];
+                        const float x1 = bhi[0] - blo[0], y1 = bhi[1] - blo[1], z1 = bhi[2] - blo[2];
+                        cost = (x0 * y0 + y0 * z0 + z0 * x0) * (float)na + (x1 * y1 + y1 * z1 + z1 * x1) * (float)(cnt - na);
                     }
-                    // the right side of the plane after bin `lane` is the inclusive suffix of lane + 1
-                    const int rc = __shfl_down_sync(0xffffffffu, sc, 1);
-                    float rlo[3], rhi[3];
-                    for (int c = 0; c < 3; ++c) {
-                        rlo[c] = __shfl_down_sync(0xffffffffu, slo[c], 1);
-                        rhi[c] = __shfl_down_sync(0xffffffffu, shi[c], 1);
-                    }
-                    if (lane < 31 && pc > 0 && rc > 0) {
-                        const float x0 = phi[0] - plo[0], y0 = phi[1] - plo[1], z0 = phi[2] - plo[2];
-                        const float x1 = rhi[0] - rlo[0], y1 = rhi[1] - rlo[1], z1 = rhi[2] - rlo[2];
-                        const float ck = (x0 * y0 + y0 * z0 + z0 * x0) * (float)pc + (x1 * y1 + y1 * z1 + z1 * x1) * (float)rc;
-                        if (ck < cost) {
-                            cost = ck;
-                            best = k * 32 + lane;
+                    int best = lane;
+                    for (int o = 4; o > 0; o >>= 1) {
+                        const float oc = __shfl_xor_sync(0xffffffffu, cost, o);
+                        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        if (oc < cost || (oc == cost && ob < best)) {
+                            cost = oc;
+                            best = ob;
                         }
                     }
-                }
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float oc = __shfl_xor_sync(0xffffffffu, cost, o);
-                    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    if (oc < cost || (oc == cost && ob < best)) {
-                        cost = oc;
-                        best = ob;
+                    best = __shfl_sync(0xffffffffu, best, 0);
+                    cost = __shfl_sync(0xffffffffu, cost, 0);
+                    unsigned bm = 1u | ((unsigned)best << 1);
+                    // no finite candidate, or an uneven split could outgrow the depth budget: halve
+                    if (!(cost < inf) || level + cnt - 1 >= s_budget) bm = (1u << (cnt / 2)) - 1u;
+                    nl = __popc(bm);
+                    if (lane < cnt) {
+                        const bool left = (bm >> lane) & 1u;
+                        const int pos = left ? __popc(bm & lt) : nl + __popc(~bm & lt);
+                        sidx[cur ^ 1][b + pos] = sidx[cur][b + lane];
                     }
+                    __syncwarp();
                 }
-                // all centroids equal (or one-sided bins), or the depth budget is used up: split the run in the middle
-                const bool median = !(cost < inf) || level + (32 - __clz(cnt - 1)) >= s_budget;
-                const int ax = best >> 5, sp = best & 31;
-                int nl = 0, nr = 0;
-                for (int base = b; base < e; base += 32) {
-                    const int i = base + lane;
-                    const bool valid = i < e;
-                    const int l = valid ? sidx[cur][i] : 0;
-                    bool go_left = false;
-                    if (valid) {
-                        if (median) go_left = (i - b) < cnt / 2;
-                        else {
-                            const float c = sbox[l][ax] + sbox[l][3 + ax];
-                            go_left = min(SAH_BINS - 1, (int)((c - cmin[ax]) * scale[ax])) <= sp;
+                else {
+                    // centroid bounds (twice the centroid: lo + hi)
+                    float cmin[3] = {inf, inf, inf}, cmax[3] = {-inf, -inf, -inf};
+                    for (int i = b + lane; i < e; i += 32) {
+                        const int l = sidx[cur][i];
+                        for (int k = 0; k < 3; ++k) {
+                            const float c = sbox[l][k] + sbox[l][3 + k];
+                            cmin[k] = fminf(cmin[k], c);
+                            cmax[k] = fmaxf(cmax[k], c);
                         }
                     }
-                    const unsigned ml = __ballot_sync(0xffffffffu, go_left), mr = __ballot_sync(0xffffffffu, valid && !go_left);
-                    if (go_left) sidx[cur ^ 1][b + nl + __popc(ml & lt)] = (unsigned short)l;
-                    else if (valid) sidx[cur ^ 1][e - 1 - (nr + __popc(mr & lt))] = (unsigned short)l;
-                    nl += __popc(ml);
-                    nr += __popc(mr);
-                }
-                __syncwarp();
-                if (lane == 0) { // emit the two children: a run of one leaf is a leaf child, a longer run a new node and task
-                    int child[2];
-                    const int cb[2] = {b, b + nl}, ce[2] = {b + nl, e};
-                    for (int sd = 0; sd < 2; ++sd) {
-                        if (ce[sd] - cb[sd] == 1) {
-                            const int k = a + sidx[cur ^ 1][cb[sd]];
-                            child[sd] = ~k;
-                            parent2[ni + k] = node;
-                        }
-                        else {
-                            const int v = atomicAdd(&s_alloc, 1);
-                            child[sd] = v;
-                            parent2[v] = node;
-                            const int q = atomicAdd(&q_n[cur ^ 1], 1);
-                            q_node[cur ^ 1][q] = v;
-                            q_b[cur ^ 1][q] = (unsigned short)cb[sd];
-                            q_e[cur ^ 1][q] = (unsigned short)ce[sd];
-                        }
+                    float scale[3];
+                    for (int k = 0; k < 3; ++k) {
+                        cmin[k] = warp_min(cmin[k]);
+                        cmax[k] = warp_max(cmax[k]);
+                        scale[k] = cmax[k] > cmin[k] ? (float)SAH_BINS / (cmax[k] - cmin[k]) : 0.f;
                     }
-                    left2[node] = child[0];
-                    right2[node] = child[1];
+                    sah_bins_clear(bins[warp], lane);
+                    __syncwarp();
+                    for (int i = b + lane; i < e; i += 32) sah_bins_add(bins[warp], sbox[sidx[cur][i]], cmin, scale);
+                    __syncwarp();
+                    float cost, whole[6];
+                    int best;
+                    sah_choose(bins[warp], lane, cost, best, whole);
+                    if (lane == 31)
+                        for (int c = 0; c < 6; ++c) node_box2[6 * node + c] = whole[c];
+                    // all centroids equal (or one-sided bins), or the depth budget is used up: split the run in the middle
+                    const bool median = !(cost < inf) || level + (32 - __clz(cnt - 1)) >= s_budget;
+                    const int ax = best >> 5, sp = best & 31;
+                    int nr = 0;
+                    for (int base = b; base < e; base += 32) {
+                        const int i = base + lane;
+                        const bool valid = i < e;
+                        const int l = valid ? sidx[cur][i] : 0;
+                        bool go_left = false;
+                        if (valid) {
+                            if (median) go_left = (i - b) < cnt / 2;
+                            else {
+                                const float c = sbox[l][ax] + sbox[l][3 + ax];
+                                go_left = min(SAH_BINS - 1, (int)((c - cmin[ax]) * scale[ax])) <= sp;
+                            }
+                        }
+                        const unsigned ml = __ballot_sync(0xffffffffu, go_left), mr = __ballot_sync(0xffffffffu, valid && !go_left);
+                        if (go_left) sidx[cur ^ 1][b + nl + __popc(ml & lt)] = (unsigned short)l;
+                        else if (valid) sidx[cur ^ 1][e - 1 - (nr + __popc(mr & lt))] = (unsigned short)l;
+                        nl += __popc(ml);
+                        nr += __popc(mr);
+                    }
+                    __syncwarp();
                 }
+                if (lane == 0) emit(node, b, nl, e);
             }
             __syncthreads();
             // leaves that were not part of a task on this level keep their place in both index buffers only if they are
             // already emitted, so nothing has to be copied; flip the buffers
-            if (threadIdx.x == 0) q_n[cur] = 0;
+            if (tid == 0) q_n[cur] = 0;
             cur ^= 1;
             ++level;
             __syncthreads();
@@ -730,6 +936,53 @@ __global__ void __launch_bounds__(TPB) k_refit(const uint64_t *__restrict__ keys
                 node_box[6 * NB * node + 6 * e + c] = fminf(l6[c], r6[c]);
                 node_box[6 * NB * node + 6 * e + 3 + c] = fmaxf(l6[3 + c], r6[3 + c]);
             }
+        }
+        node = parent[node];
+    }
+}
+
+// Refit of the traversal tree ABOVE the rebuilt subtrees, whose nodes got their boxes from k_sah_rebuild: one climber per
+// subtree root, one per leaf that no subtree covers (a leaf, or a pair of leaves, hanging directly under a node of more
+// than SAH_MAX leaves).  A scene that is one subtree needs no refit at all.
+__global__ void __launch_bounds__(TPB) k_refit_upper(const uint64_t *__restrict__ keys, int n, const int *__restrict__ left,
+                                                      const int *__restrict__ right, const int *__restrict__ parent,
+                                                      const int *__restrict__ canon_parent, const int2 *__restrict__ range,
+                                                      const float *__restrict__ prim_box, const int *__restrict__ roots,
+                                                      const SahState *st, float *node_box, int *visit)
+{
+    const int k = blockIdx.x * TPB + threadIdx.x;
+    const int ni = n - 1;
+    int node;
+    if (k < n) {
+        // covered by a rebuilt subtree <=> some ancestor has 3 .. SAH_MAX leaves; sizes grow upwards, so it is the parent or,
+        // under a parent of two leaves, the grandparent -- in the CANONICAL tree, whose ranges `range` holds (the parts of
+        // the traversal tree that no subtree covers kept the canonical links)
+        int p = canon_parent[ni + k];
+        int size = range[p].y - range[p].x + 1;
+        if (size == 2 && canon_parent[p] >= 0) {
+            p = canon_parent[p];
+            size = range[p].y - range[p].x + 1;
+        }
+        if (size >= 3 && size <= SAH_MAX) return;
+        node = parent[ni + k];
+    }
+    else if (k - n < st->n_roots) node = parent[roots[k - n]];
+    else return;
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&visit[node], 1) == 0) return;
+        __threadfence();
+        const int L = left[node], R = right[node];
+        const volatile float *lb = L >= 0 ? node_box + 6 * L : nullptr;
+        const volatile float *rb = R >= 0 ? node_box + 6 * R : nullptr;
+        float l6[6], r6[6];
+        for (int c = 0; c < 6; ++c) {
+            l6[c] = L >= 0 ? lb[c] : prim_box[6 * (uint32_t)keys[~L] + c];
+            r6[c] = R >= 0 ? rb[c] : prim_box[6 * (uint32_t)keys[~R] + c];
+        }
+        for (int c = 0; c < 3; ++c) {
+            node_box[6 * node + c] = fminf(l6[c], r6[c]);
+            node_box[6 * node + 3 + c] = fmaxf(l6[3 + c], r6[3 + c]);
         }
         node = parent[node];
     }
@@ -978,7 +1231,8 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
     const int n_seg = (n + SEG - 1) / SEG;
     const int sort_blocks = (n_seg + SORT_WARPS - 1) / SORT_WARPS;
     uint64_t *src = ctx->d_keys, *dst = ctx->d_keys_tmp;
-    for (int pass = 0; pass < 4; ++pass) {
+    if (n <= SMALL_SORT) k_sort_small<<<1, 1024, 0, st>>>(ctx->d_keys, n);
+    else for (int pass = 0; pass < 4; ++pass) {
         const int shift = 32 + 8 * pass;
         k_hist<<<sort_blocks, TPB, 0, st>>>(src, n, shift, n_seg, ctx->d_hist);
         const int hist_len = 256 * n_seg, scan_blocks = (hist_len + SCAN_CHUNK - 1) / SCAN_CHUNK;
@@ -999,26 +1253,39 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
     const float *t_node_box = ctx->d_node_box;
     if (n > 1) {
         const int nbi = (n - 1 + TPB - 1) / TPB;
-        RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_visit, 0, sizeof(int) * (size_t)(n - 1), st));
         k_karras<<<nbi, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_range);
-        k_refit<1><<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_prim_box,
-                                       ctx->d_node_box, ctx->d_visit);
         const int *t_parent = ctx->d_parent;
+        RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_visit, 0, sizeof(int) * (size_t)(n - 1), st));
         if (n >= 3) { // SAH rebuild of every subtree of <= SAH_MAX leaves, for the traversal tree only
             SahState *ss = (SahState *)(ctx->d_collapse + 8);
             RRTB_CUDA(ctx, cudaMemsetAsync(ss, 0, sizeof(SahState), st));
             k_sah_select<<<(2 * n - 1 + TPB - 1) / TPB, TPB, 0, st>>>(n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_range, ctx->d_left2,
                                                                        ctx->d_right2, ctx->d_parent2, ctx->d_sah_roots, ss);
             const int max_roots = 2 * ((n + SAH_MAX - 1) / SAH_MAX) + 1; // maximal subtrees are disjoint and each parent covers > SAH_MAX leaves
-            k_sah_rebuild<<<min(max_roots, ctx->sm_count * 4), SAH_TPB, 0, st>>>(ctx->d_keys, n, ctx->d_range, ctx->d_prim_box, ctx->d_sah_roots,
-                                                                                 ctx->d_parent, ss, ctx->d_left2, ctx->d_right2, ctx->d_parent2);
-            RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_visit, 0, sizeof(int) * (size_t)(n - 1), st));
-            k_refit<1><<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left2, ctx->d_right2, ctx->d_parent2, ctx->d_prim_box,
-                                           ctx->d_node_box2, ctx->d_visit);
+            constexpr int SAH_BINS_BYTES = 3 * SAH_BINS * 7 * (int)sizeof(int); // per warp
+            if (n <= 8 * SAH_MAX) {
+                RRTB_CUDA(ctx, cudaFuncSetAttribute(k_sah_rebuild<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * SAH_BINS_BYTES));
+                k_sah_rebuild<1024><<<min(max_roots, ctx->sm_count), 1024, 32 * SAH_BINS_BYTES, st>>>(
+                    ctx->d_keys, n, ctx->d_range, ctx->d_prim_box, ctx->d_sah_roots, ctx->d_parent, ss, ctx->d_left2, ctx->d_right2, ctx->d_parent2,
+                    ctx->d_node_box2);
+            }
+            else
+                k_sah_rebuild<256><<<min(max_roots, ctx->sm_count * 4), 256, 8 * SAH_BINS_BYTES, st>>>(
+                    ctx->d_keys, n, ctx->d_range, ctx->d_prim_box, ctx->d_sah_roots, ctx->d_parent, ss, ctx->d_left2, ctx->d_right2, ctx->d_parent2,
+                    ctx->d_node_box2);
+            k_refit_upper<<<(n + max_roots + TPB - 1) / TPB, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left2, ctx->d_right2, ctx->d_parent2, ctx->d_parent, ctx->d_range,
+                                                                            ctx->d_prim_box, ctx->d_sah_roots, ss, ctx->d_node_box2, ctx->d_visit);
             t_left = ctx->d_left2;
             t_right = ctx->d_right2;
             t_parent = ctx->d_parent2;
             t_node_box = ctx->d_node_box2;
+            // the boxes of the canonical tree are needed by rrtb_bvh_download only: refit_canonical() on demand
+            ctx->canonical_boxes = false;
+        }
+        else {
+            k_refit<1><<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_prim_box,
+                                           ctx->d_node_box, ctx->d_visit);
+            ctx->canonical_boxes = true;
         }
         if (ctx->motion) { // boxes at the two ends of the shutter, for the interpolating traversal nodes
             RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_visit, 0, sizeof(int) * (size_t)(n - 1), st));
@@ -1040,6 +1307,21 @@ int prepare_and_build(rrtb_ctx *ctx, const rrtb_sphere *d_sph, const rrtb_mspher
     k_flatten_leaves<<<nb, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_prim, ctx->d_prim_info, has_ext ? ctx->d_prim_ext : nullptr, ctx->d_leaves,
                                          ctx->d_leaf_info, has_ext ? ctx->d_leaf_ext : nullptr);
     RRTB_CUDA(ctx, cudaGetLastError());
+    return RRTB_OK;
+}
+
+// Boxes of the canonical LBVH (rrtb_bvh_download; the traversal tree has its own): refit once, when first asked for.
+int refit_canonical(rrtb_ctx *ctx)
+{
+    const int n = ctx->n_prims;
+    if (ctx->canonical_boxes || n < 2) return RRTB_OK;
+    cudaStream_t st = ctx->stream;
+    RRTB_CUDA(ctx, cudaMemsetAsync(ctx->d_visit, 0, sizeof(int) * (size_t)(n - 1), st));
+    k_refit<1><<<(n + TPB - 1) / TPB, TPB, 0, st>>>(ctx->d_keys, n, ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_prim_box,
+                                                    ctx->d_node_box, ctx->d_visit);
+    RRTB_CUDA(ctx, cudaGetLastError());
+    RRTB_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->canonical_boxes = true;
     return RRTB_OK;
 }
 

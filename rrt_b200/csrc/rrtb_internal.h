@@ -38,6 +38,7 @@ struct rrtb_ctx {
     int *d_left = nullptr, *d_right = nullptr; // [n-1]
     int *d_parent = nullptr;        // [2n-1]
     float *d_node_box = nullptr;    // [6(n-1)]
+    bool canonical_boxes = false;   // d_node_box holds the refit of the canonical tree (else: refit_canonical on demand)
     // scenes with motion (moving primitives and an open shutter): boxes at the two ends of the shutter, for the
     // interpolating traversal nodes (rrtb_device.cuh "Motion node")
     bool motion = false;
@@ -82,6 +83,7 @@ struct rrtb_ctx {
     bool peer_is_ipc = false;
     void *h_pinned = nullptr;                 // pinned staging for device->host copies into pageable user buffers
     size_t h_pinned_bytes = 0;
+    int *h_state = nullptr;                   // pinned: CollapseState read back behind every build
     // Device buffers are grow-only: rrtb_scene_set re-uses them when the next scene fits (a frame loop that re-sends
     // its scene pays no cudaMalloc / cudaFree).  Capacity in bytes, keyed by the address of the pointer member.
     std::unordered_map<const void *, size_t> capacity;
@@ -100,6 +102,7 @@ int cuda_fail(rrtb_ctx *ctx, cudaError_t e, const char *expr, const char *file, 
 
 // rrtb_bvh.cu
 void free_scene(rrtb_ctx *ctx);
+int refit_canonical(rrtb_ctx *ctx);
 
 // rrtb_render.cu
 DeviceScene device_scene(const rrtb_ctx *ctx);
