@@ -268,7 +268,7 @@ int rrtb_bvh_download(rrtb_ctx *ctx, uint32_t *morton, uint32_t *perm, int32_t *
                       int32_t *parent, float *node_box, float *prim_box);
 /* The traversal tree the render kernels walk: the 4-wide collapse of the canonical LBVH above (greedy by surface
  * area); *width = 4.  32 floats per node: c.x[4] c.y[4] c.z[4] h.x[4] h.y[4] h.z[4] (padded child boxes as centre /
- * half extent; on the device the half extents are bf16 rounded up and a node is 96 bytes -- this call hands them back
+ * half extent; on the device the half extents are fp16 rounded up and a node is 96 bytes -- this call hands them back
  * widened to float), 4 child refs as int bits, 4 unused.  Child ref >= 0: node index; < 0: ~((sorted position << 2) |
  * primitive type); an unused child slot has h = -inf.  Node 0 is the root; a parent always precedes its children.
  * Test hook: the tree is derived data (closest hit does not depend on it); it is checked for being a partition of

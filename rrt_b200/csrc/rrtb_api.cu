@@ -855,6 +855,24 @@ int rrtb_wide_size(rrtb_ctx *ctx, int32_t *n_nodes, int32_t *width)
     return RRTB_OK;
 }
 
+// IEEE half precision -> float (the half extents of the traversal nodes, rrtb_device.cuh "Traversal node")
+static float f16_to_float(uint16_t h)
+{
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 31u, m = h & 1023u;
+    uint32_t b;
+    if (e == 31u) b = sign | 0x7f800000u | (m << 13);            // inf / nan
+    else if (e != 0u) b = sign | ((e + 112u) << 23) | (m << 13); // normal
+    else if (m == 0u) b = sign;                                  // zero
+    else {                                                       // subnormal: m * 2^-24
+        float x = (float)m * 5.9604644775390625e-08f;
+        memcpy(&b, &x, 4);
+        b |= sign;
+    }
+    float x;
+    memcpy(&x, &b, 4);
+    return x;
+}
+
 int rrtb_wide_download(rrtb_ctx *ctx, float *nodes, int32_t max_nodes)
 {
     if (!ctx || !nodes || max_nodes < 0) return RRTB_ERR_INVALID;
@@ -862,7 +880,7 @@ int rrtb_wide_download(rrtb_ctx *ctx, float *nodes, int32_t max_nodes)
     int rc = rrtb_wide_size(ctx, &n_nodes, nullptr);
     if (rc) return rc;
     if (n_nodes > max_nodes) return invalid(ctx, "wide-node buffer too small");
-    // device nodes are 24 words with bf16 half extents (rrtb_device.cuh "Traversal node"), or 40 words with the boxes at
+    // device nodes are 24 words with fp16 half extents (rrtb_device.cuh "Traversal node"), or 40 words with the boxes at
     // both ends of the shutter ("Motion node"); hand them back decoded, the motion node as the UNION of its two boxes
     const int words = ctx->motion ? 40 : 24;
     std::vector<uint32_t> raw((size_t)words * n_nodes);
@@ -879,7 +897,7 @@ int rrtb_wide_download(rrtb_ctx *ctx, float *nodes, int32_t max_nodes)
         for (int axis = 0; axis < 3; ++axis)
             for (int c = 0; c < 4; ++c) {
                 const int pw = 2 * axis + c / 2; // the pair word of (axis, child pair)
-                auto half = [&](int base) { return (c & 1) ? f(w[base + pw] & 0xffff0000u) : f(w[base + pw] << 16); };
+                auto half = [&](int base) { return f16_to_float((uint16_t)((c & 1) ? w[base + pw] >> 16 : w[base + pw] & 0xffffu)); };
                 float c0 = f(w[4 * axis + c]), h0 = half(hbase);
                 if (ctx->motion) {
                     const float c1 = f(w[12 + 4 * axis + c]), h1 = half(hbase + 6);

@@ -19,6 +19,8 @@
 // permutation and the topology are BIT-EXACT against oracle/rrt_oracle.c (tests/test_lbvh_parity.py).
 #include "rrtb_internal.h"
 
+#include <cuda_fp16.h>
+
 #include <math.h>
 #include <stdio.h>
 
@@ -74,6 +76,15 @@ __global__ void __launch_bounds__(TPB) k_prepare(const rrtb_sphere *__restrict__
         if (id < ns) {
             rrtb_sphere s = sph[id];
             a = make_float4(s.center[0], s.center[1], s.center[2], s.radius);
+            {
+                // centre and radius once more as doubles, for the leaf test (rrtb_device.cuh sphere_test_d4): the record has
+                // 32 spare bytes and the conversion (exact) then happens here instead of at every test
+                const double d[4] = {(double)s.center[0], (double)s.center[1], (double)s.center[2], (double)s.radius};
+                b = make_float4(__int_as_float(__double2loint(d[0])), __int_as_float(__double2hiint(d[0])),
+                                __int_as_float(__double2loint(d[1])), __int_as_float(__double2hiint(d[1])));
+                c = make_float4(__int_as_float(__double2loint(d[2])), __int_as_float(__double2hiint(d[2])),
+                                __int_as_float(__double2loint(d[3])), __int_as_float(__double2hiint(d[3])));
+            }
             mat = s.material;
             // sphere.h:60-64 with |radius|: the reference's center -+ radius is an INVERTED box for the negative radii the
             // book uses for hollow glass (its bvh then loses the sphere while the flat scan renders it); for radius >= 0
@@ -1029,16 +1040,10 @@ __global__ void __launch_bounds__(TPB) k_collapse_init(int *__restrict__ wq, int
     }
 }
 
-// half extents travel as bf16 ROUNDED UP (a box may only grow); -inf (unused slot) is exact
-__device__ __forceinline__ unsigned bf16_up(float h)
-{
-    const unsigned b = __float_as_uint(h);
-    return (b & 0x80000000u) ? (b >> 16) : ((b + 0xffffu) >> 16); // h >= 0 (or -inf): next bf16 at or above h
-}
-__device__ __forceinline__ float bf16_pair_up(float lo, float hi)
-{
-    return __uint_as_float(bf16_up(lo) | (bf16_up(hi) << 16));
-}
+// half extents travel as IEEE half precision (fp16) ROUNDED UP (a box may only grow: by < 2^-10 of its half extent, by at
+// most 6e-8 below the smallest normal half, to +inf -- a slab that always passes -- above 65504); -inf (unused slot) is exact
+__device__ __forceinline__ unsigned f16_up(float h) { return (unsigned)__half_as_ushort(__float2half_ru(h)); }
+__device__ __forceinline__ float f16_pair_up(float lo, float hi) { return __uint_as_float(f16_up(lo) | (f16_up(hi) << 16)); }
 
 __device__ __forceinline__ float box_area6(const float *b)
 {
@@ -1116,7 +1121,7 @@ __device__ __forceinline__ void collapse_one(int i, int b, const uint64_t *__res
         }
     }
     if (motion) {
-        // 160-byte motion node (rrtb_device.cuh "Motion node"): centres at both ends of the shutter, bf16 half extents
+        // 160-byte motion node (rrtb_device.cuh "Motion node"): centres at both ends of the shutter, fp16 half extents
         // (rounded up) at both ends, refs; the traversal interpolates box(s) = (1 - s) box0 + s box1
         float4 *w = wnodes + RRTB_MOTION_NODE_F4 * (size_t)i;
         w[0] = make_float4(cx[0], cx[1], cx[2], cx[3]);
@@ -1125,19 +1130,19 @@ __device__ __forceinline__ void collapse_one(int i, int b, const uint64_t *__res
         w[3] = make_float4(c1x[0], c1x[1], c1x[2], c1x[3]);
         w[4] = make_float4(c1y[0], c1y[1], c1y[2], c1y[3]);
         w[5] = make_float4(c1z[0], c1z[1], c1z[2], c1z[3]);
-        w[6] = make_float4(bf16_pair_up(hx[0], hx[1]), bf16_pair_up(hx[2], hx[3]), bf16_pair_up(hy[0], hy[1]), bf16_pair_up(hy[2], hy[3]));
-        w[7] = make_float4(bf16_pair_up(hz[0], hz[1]), bf16_pair_up(hz[2], hz[3]), bf16_pair_up(h1x[0], h1x[1]), bf16_pair_up(h1x[2], h1x[3]));
-        w[8] = make_float4(bf16_pair_up(h1y[0], h1y[1]), bf16_pair_up(h1y[2], h1y[3]), bf16_pair_up(h1z[0], h1z[1]), bf16_pair_up(h1z[2], h1z[3]));
+        w[6] = make_float4(f16_pair_up(hx[0], hx[1]), f16_pair_up(hx[2], hx[3]), f16_pair_up(hy[0], hy[1]), f16_pair_up(hy[2], hy[3]));
+        w[7] = make_float4(f16_pair_up(hz[0], hz[1]), f16_pair_up(hz[2], hz[3]), f16_pair_up(h1x[0], h1x[1]), f16_pair_up(h1x[2], h1x[3]));
+        w[8] = make_float4(f16_pair_up(h1y[0], h1y[1]), f16_pair_up(h1y[2], h1y[3]), f16_pair_up(h1z[0], h1z[1]), f16_pair_up(h1z[2], h1z[3]));
         w[9] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
     }
     else {
-        // 96-byte node (rrtb_device.cuh "Traversal node"): float centres, bf16 half extents rounded up, refs
+        // 96-byte node (rrtb_device.cuh "Traversal node"): float centres, fp16 half extents rounded up, refs
         float4 *w = wnodes + RRTB_NODE_F4 * (size_t)i;
         w[0] = make_float4(cx[0], cx[1], cx[2], cx[3]);
         w[1] = make_float4(cy[0], cy[1], cy[2], cy[3]);
         w[2] = make_float4(cz[0], cz[1], cz[2], cz[3]);
-        w[3] = make_float4(bf16_pair_up(hx[0], hx[1]), bf16_pair_up(hx[2], hx[3]), bf16_pair_up(hy[0], hy[1]), bf16_pair_up(hy[2], hy[3]));
-        w[4] = make_float4(bf16_pair_up(hz[0], hz[1]), bf16_pair_up(hz[2], hz[3]), __int_as_float(ref[0]), __int_as_float(ref[1]));
+        w[3] = make_float4(f16_pair_up(hx[0], hx[1]), f16_pair_up(hx[2], hx[3]), f16_pair_up(hy[0], hy[1]), f16_pair_up(hy[2], hy[3]));
+        w[4] = make_float4(f16_pair_up(hz[0], hz[1]), f16_pair_up(hz[2], hz[3]), __int_as_float(ref[0]), __int_as_float(ref[1]));
         w[5] = make_float4(__int_as_float(ref[2]), __int_as_float(ref[3]), 0.f, 0.f);
     }
     if (leaves) {

@@ -37,7 +37,7 @@ __device__ unsigned int g_rrtb_violations;
 // ---- scene as the kernels see it -----------------------------------------------------------------
 // Leaf record: 3 x float4 (48 B) per primitive, in LEAF ORDER (Morton order for the LBVH, object-id
 // order for the flat scan):
-//   sphere         a = (c.xyz, r)
+//   sphere         a = (c.xyz, r)    b = (double c.x, double c.y)  c = (double c.z, double r)   (the same values, converted once)
 //   moving sphere  a = (c0.xyz, r)   b = (c1-c0 .xyz, t0)   c = (t1-t0, -, -, -)
 //   triangle       a = (v0.xyz, n.x) b = (e1.xyz, n.y)      c = (e2.xyz, n.z)    n = unit face normal
 //   moving tri.    a = (base.xyz, rate.x) b = (e1 base.xyz, rate.y) c = (e2 base.xyz, rate.z)   v0(time) = fma(rate, time, base)
@@ -46,11 +46,11 @@ __device__ unsigned int g_rrtb_violations;
 //                  (include/rrtb.h "rrtb_mtriangle"; the normal is that of the pose at the ray's time)
 // leaf_info[k] = (object id, material index)
 // Traversal node: a 4-WIDE node collapsed from the canonical binary LBVH (rrtb_bvh.cu k_collapse4), 24 words (96 B,
-// read with three 256-bit loads): the padded boxes of the four children as centre c (float) and half extent h (bf16,
-// rounded UP: the box only grows, by < 0.8 % of its half extent) and the four child refs:
+// read with three 256-bit loads): the padded boxes of the four children as centre c (float) and half extent h (fp16,
+// rounded UP: the box only grows, by < 0.1 % of its half extent; +inf above 65504) and the four child refs:
 //   words  0-11  c.x[0..3]  c.y[0..3]  c.z[0..3]
-//   words 12-17  h.x(0,1) h.x(2,3) h.y(0,1) h.y(2,3) h.z(0,1) h.z(2,3): two bf16 per word, child 2k in the low half --
-//                one shift and one mask turn a word into the FP32x2 pair that FFMA2 takes
+//   words 12-17  h.x(0,1) h.x(2,3) h.y(0,1) h.y(2,3) h.z(0,1) h.z(2,3): two fp16 per word, child 2k in the low half --
+//                two HADD2.F32 (fma pipe) turn a word into the FP32x2 pair that FFMA2 takes
 //   words 18-21  bits(child ref[0..3])      words 22-23 unused
 // The render kernels are bound by the l1tex data stage (ncu: 81-87 % of its peak), which spends a cycle per load
 // instruction and 128-byte line touched: the 128-byte all-float node of the first version cost four of them per lane
@@ -264,11 +264,16 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
     return r;
 }
 
-// two bf16 in one word -> the FP32x2 pair (low half first): a shift and a mask
-__device__ __forceinline__ f32x2 bf16x2(float word)
+// two fp16 in one word -> the FP32x2 pair (low half first): two HADD2.F32 (one per half, operand swizzle .H0_H0 / .H1_H1),
+// which run on the fma pipe -- the bf16 pairs of the first 96-byte node cost a shift and a LOP3 per word on the alu pipe,
+// the pipe that bounds a node visit (profiles/README.md)
+__device__ __forceinline__ f32x2 half2x2(float word)
 {
-    const unsigned w = __float_as_uint(word);
-    return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+    float lo, hi;
+    asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}"
+        : "=f"(lo), "=f"(hi)
+        : "r"(__float_as_uint(word)));
+    return pack2(lo, hi);
 }
 
 // Slab test of TWO children of a wide node at once (already padded boxes as centre c and half extent h; each
@@ -303,16 +308,18 @@ __device__ __forceinline__ void box_hit_pair(f32x2 cx, f32x2 cy, f32x2 cz, f32x2
 // ---- primitive tests (bit-exact vs oracle sphere_roots / triangle_t) ---------------------------------------
 // sphere.h:33-58: nearest root in [t_min, t_max], inclusive.  oc, half_b, c and the discriminant in
 // double (the cancellation-prone part), roots in float via the cancellation-free pair q/a, c/q.
-__device__ __forceinline__ bool sphere_test(const Ray &r, const RayPre &p, float cx, float cy, float cz, float rad,
-                                            float t_min, float t_max, float &t_out)
+// (cx, cy, cz, rr): centre and radius in double -- exact conversions of the float scene values, which static spheres carry
+// in the 32 spare bytes of their leaf record so that the test converts only the ray (6 instead of 10 F2F on the XU pipe,
+// the pipe that bounds a sphere test: 17 XU instructions of 8 cycles each in ~75)
+__device__ __forceinline__ bool sphere_test_d4(const Ray &r, double cx, double cy, double cz, double rr, float t_min,
+                                               float t_max, float &t_out)
 {
-    double ocx = __dsub_rn((double)r.ox, (double)cx);
-    double ocy = __dsub_rn((double)r.oy, (double)cy);
-    double ocz = __dsub_rn((double)r.oz, (double)cz);
+    double ocx = __dsub_rn((double)r.ox, cx);
+    double ocy = __dsub_rn((double)r.oy, cy);
+    double ocz = __dsub_rn((double)r.oz, cz);
     double dx = r.dx, dy = r.dy, dz = r.dz;
     double a = __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
     double hb = __fma_rn(ocz, dz, __fma_rn(ocy, dy, __dmul_rn(ocx, dx)));
-    double rr = rad;
     double cc = __fma_rn(-rr, rr, __fma_rn(ocz, ocz, __fma_rn(ocy, ocy, __dmul_rn(ocx, ocx))));
     double disc = __fma_rn(-a, cc, __dmul_rn(hb, hb));
     if (disc < 0.0) return false;
@@ -328,6 +335,11 @@ __device__ __forceinline__ bool sphere_test(const Ray &r, const RayPre &p, float
     }
     t_out = root;
     return true;
+}
+__device__ __forceinline__ bool sphere_test(const Ray &r, const RayPre &, float cx, float cy, float cz, float rad,
+                                            float t_min, float t_max, float &t_out)
+{
+    return sphere_test_d4(r, (double)cx, (double)cy, (double)cz, (double)rad, t_min, t_max, t_out);
 }
 
 // moving_sphere.h:27-30
@@ -450,20 +462,23 @@ __device__ __forceinline__ void leaf_test(const float4 *__restrict__ leaves, con
         else ++cnt.tri;
     }
     const float4 *rec = leaves + (size_t)(unsigned)slot * 3u; // one IMAD.WIDE (slot * 48 + base)
-    float4 a = __ldg(rec);
     float t;
     bool h;
-    if (type == PRIM_SPHERE) {
-        h = sphere_test(r, p, a.x, a.y, a.z, a.w, t_min, best.t, t);
+    if (type == PRIM_SPHERE) { // centre and radius as doubles in the second and third float4 (k_prepare)
+        const float4 b = __ldg(rec + 1), c = __ldg(rec + 2);
+        h = sphere_test_d4(r, __hiloint2double(__float_as_int(b.y), __float_as_int(b.x)),
+                           __hiloint2double(__float_as_int(b.w), __float_as_int(b.z)),
+                           __hiloint2double(__float_as_int(c.y), __float_as_int(c.x)),
+                           __hiloint2double(__float_as_int(c.w), __float_as_int(c.z)), t_min, best.t, t);
     }
     else if (type == PRIM_MSPHERE) {
-        float4 b = __ldg(rec + 1), c = __ldg(rec + 2);
+        float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
         float cx, cy, cz;
         msphere_center(a, b, c, r.tm, cx, cy, cz);
         h = sphere_test(r, p, cx, cy, cz, a.w, t_min, best.t, t);
     }
     else {
-        float4 b = __ldg(rec + 1), c = __ldg(rec + 2);
+        float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
         double v0x = a.x, v0y = a.y, v0z = a.z;
         if (MTRI && type == PRIM_MTRIANGLE) { // the instance moves: meet the triangle of the pose at the ray's time
             double tm = r.tm;
@@ -507,17 +522,19 @@ __device__ __forceinline__ Hit closest_scan(const DeviceScene &s, const Ray &r, 
 //                     nearest hit child is next, the other hit children are pushed
 //   cur <  0          a leaf reference        -> leaf_step: exact primitive test, then pop
 //   cur == TRAV_DONE  traversal finished
-// Every child that is hit gets a KEY = the bits of its entry distance with the two low mantissa bits replaced by
-// its slot: non-negative floats order as integers, so the nearest child is one 4-input unsigned minimum (2 VIMNMX3),
-// its slot comes with it, and equal distances can not tie.  The other hit children are pushed in slot order.
+// Every child that is hit gets a KEY = the bits of its entry distance with the low mantissa BYTE replaced by its slot
+// (one PRMT; the 15 mantissa bits that remain order the children): non-negative floats order as integers, so the nearest
+// child is one 4-input unsigned minimum (2 VIMNMX3), its slot comes with it, and equal distances can not tie.  The other
+// hit children are pushed in slot order.  A visit is branch-free: pushes, selection and the pop of a visit that hit no
+// child are predicated instructions (the branch around the pushes diverged in most warps and cost five instructions).
 // Measured and dropped (profiles/README.md, round 2): pushing the keys with the references so that a leaf whose
 // entry distance already exceeds the closest hit is skipped at pop time (-12 % leaf tests, but twice the local-memory
 // traffic: 5 % slower), a full sort of the hit children (more instructions than the visits it saves), and the
 // binary tree itself (two children per node: 3 % slower on the headline scene, 10 % on the 1.1 M-primitive one).
 // A collapsed tree is never deeper than the binary tree it comes from: <= 62 levels for the Karras tree (30-bit
 // Morton codes with an index tie-break), and the SAH rebuild of its lower subtrees (rrtb_bvh.cu k_sah_rebuild) keeps
-// every leaf within 63 levels; a visit pushes at most three entries, so 192 entries can not overflow.  The entries
-// live in local memory (L1-resident).
+// every leaf within 63 levels; a visit pushes at most three entries, so 192 entries (one of them the TRAV_DONE at the
+// bottom) can not overflow.  The entries live in local memory (L1-resident).
 #define RRTB_WIDTH 4
 #define RRTB_NODE_F4 6 // float4 per traversal node (96 B)
 #define RRTB_MOTION_NODE_F4 10 // float4 per motion node (160 B)
@@ -533,10 +550,71 @@ __device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b)
         : "l"(p));
 }
 
-__device__ __forceinline__ void trav_pop(int &cur, int &sp, const int *stk)
+// The stack grows upwards from stk[1]; stk[0] holds TRAV_DONE, so the pop that empties the stack ends the traversal
+// without a test.  TravSp points at the next free entry (a local-memory address kept in a register instead of an index
+// that every access scales and adds to the frame: 218 -> 196 SASS instructions per two visits together with the
+// branch-free visit and the PRMT keys).  -DRRTB_TRAV_LEGACY / -DRRTB_KEY_LOW2 build the round-1 forms for A/B runs.
+#ifndef RRTB_TRAV_LEGACY
+#ifdef RRTB_TRAV_ASM
+// the same with the stack pointer as a 32-bit .local address and every access in PTX, so that a conditional push is
+// exactly a predicated STL and a predicated add (nvcc's if-conversion of `if (c) *sp++ = ref` costs a third instruction)
+typedef unsigned TravSp;
+__device__ __forceinline__ void trav_pop(int &cur, TravSp &sp, const int *)
 {
-    cur = sp > 0 ? stk[--sp] : TRAV_DONE;
+    asm volatile("ld.local.b32 %0, [%1+-4];\n\tadd.u32 %1, %1, -4;" : "=r"(cur), "+r"(sp));
 }
+__device__ __forceinline__ void trav_pop_if_neg(int m, int &cur, TravSp &sp, const int *) // if (m < 0) pop
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, 0;\n\t@p ld.local.b32 %0, [%1+-4];\n\t@p add.u32 %1, %1, -4;\n\t}"
+                 : "+r"(cur), "+r"(sp)
+                 : "r"(m));
+}
+__device__ __forceinline__ void trav_push_if_gt(int k, int m, TravSp &sp, int *, int ref) // if (k > m) push ref
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %2, %3;\n\t@p st.local.b32 [%0], %1;\n\t@p add.u32 %0, %0, 4;\n\t}"
+                 : "+r"(sp)
+                 : "r"(ref), "r"(k), "r"(m));
+}
+__device__ __forceinline__ void trav_begin(int &cur, TravSp &sp, int *stk)
+{
+    cur = 0;
+    sp = (unsigned)__cvta_generic_to_local(stk);
+    asm volatile("st.local.b32 [%0], %1;\n\tadd.u32 %0, %0, 4;" : "+r"(sp) : "r"(TRAV_DONE));
+}
+__device__ __forceinline__ int trav_depth(TravSp sp, const int *stk) { return (int)(sp - (unsigned)__cvta_generic_to_local(stk)) >> 2; }
+#else
+typedef int *TravSp;
+__device__ __forceinline__ void trav_pop(int &cur, TravSp &sp, const int *) { cur = *--sp; }
+__device__ __forceinline__ void trav_pop_if_neg(int m, int &cur, TravSp &sp, const int *)
+{
+    if (m < 0) cur = *--sp;
+}
+__device__ __forceinline__ void trav_push_if_gt(int k, int m, TravSp &sp, int *, int ref)
+{
+    if (k > m) *sp++ = ref;
+}
+__device__ __forceinline__ void trav_begin(int &cur, TravSp &sp, int *stk)
+{
+    cur = 0;
+    stk[0] = TRAV_DONE;
+    sp = stk + 1;
+}
+__device__ __forceinline__ int trav_depth(TravSp sp, const int *stk) { return (int)(sp - stk); }
+#endif
+#else
+typedef int TravSp;
+__device__ __forceinline__ void trav_pop(int &cur, TravSp &sp, const int *stk) { cur = sp > 0 ? stk[--sp] : TRAV_DONE; }
+__device__ __forceinline__ void trav_push_if_gt(int k, int m, TravSp &sp, int *stk, int ref)
+{
+    if (k > m) stk[sp++] = ref;
+}
+__device__ __forceinline__ void trav_begin(int &cur, TravSp &sp, int *)
+{
+    cur = 0;
+    sp = 0;
+}
+__device__ __forceinline__ int trav_depth(TravSp sp, const int *) { return sp; }
+#endif
 
 // t_min must be >= 0 (keys order as integers only for non-negative distances); rrtb_trace_closest checks it
 // (1 - s) a + s b on an FP32x2 pair
@@ -547,7 +625,7 @@ __device__ __forceinline__ f32x2 lerp2(f32x2 a, f32x2 b, float s, float oms)
 
 template <bool COUNT, bool MOTION = false>
 __device__ __forceinline__ void wide_step(const float4 *__restrict__ wnodes, const RayPre &p, float t_min, float t_max,
-                                          int &cur, int &sp, int *stk, TravCounters &cnt)
+                                          int &cur, TravSp &sp, int *stk, TravCounters &cnt)
 {
     if (COUNT) cnt.box += RRTB_WIDTH;
     bool h0, h1, h2, h3;
@@ -559,55 +637,70 @@ __device__ __forceinline__ void wide_step(const float4 *__restrict__ wnodes, con
         ldg256(q, ax, ay);     // c0.x[4] c0.y[4]
         ldg256(q + 2, az, bx); // c0.z[4] c1.x[4]
         ldg256(q + 4, by, bz); // c1.y[4] c1.z[4]
-        ldg256(q + 6, g0, g1); // bf16 pairs h0.x(0,1) h0.x(2,3) h0.y(0,1) h0.y(2,3) | h0.z(0,1) h0.z(2,3) h1.x(0,1) h1.x(2,3)
-        ldg256(q + 8, g2, rr); // bf16 pairs h1.y(0,1) h1.y(2,3) h1.z(0,1) h1.z(2,3) | refs
+        ldg256(q + 6, g0, g1); // fp16 pairs h0.x(0,1) h0.x(2,3) h0.y(0,1) h0.y(2,3) | h0.z(0,1) h0.z(2,3) h1.x(0,1) h1.x(2,3)
+        ldg256(q + 8, g2, rr); // fp16 pairs h1.y(0,1) h1.y(2,3) h1.z(0,1) h1.z(2,3) | refs
         rf = make_int4(__float_as_int(rr.x), __float_as_int(rr.y), __float_as_int(rr.z), __float_as_int(rr.w));
         const float s = p.s, oms = 1.0f - p.s;
         box_hit_pair(lerp2(pack2(ax.x, ax.y), pack2(bx.x, bx.y), s, oms), lerp2(pack2(ay.x, ay.y), pack2(by.x, by.y), s, oms),
-                     lerp2(pack2(az.x, az.y), pack2(bz.x, bz.y), s, oms), lerp2(bf16x2(g0.x), bf16x2(g1.z), s, oms),
-                     lerp2(bf16x2(g0.z), bf16x2(g2.x), s, oms), lerp2(bf16x2(g1.x), bf16x2(g2.z), s, oms), p, t_min, t_max, h0, h1, t0, t1);
+                     lerp2(pack2(az.x, az.y), pack2(bz.x, bz.y), s, oms), lerp2(half2x2(g0.x), half2x2(g1.z), s, oms),
+                     lerp2(half2x2(g0.z), half2x2(g2.x), s, oms), lerp2(half2x2(g1.x), half2x2(g2.z), s, oms), p, t_min, t_max, h0, h1, t0, t1);
         box_hit_pair(lerp2(pack2(ax.z, ax.w), pack2(bx.z, bx.w), s, oms), lerp2(pack2(ay.z, ay.w), pack2(by.z, by.w), s, oms),
-                     lerp2(pack2(az.z, az.w), pack2(bz.z, bz.w), s, oms), lerp2(bf16x2(g0.y), bf16x2(g1.w), s, oms),
-                     lerp2(bf16x2(g0.w), bf16x2(g2.y), s, oms), lerp2(bf16x2(g1.y), bf16x2(g2.w), s, oms), p, t_min, t_max, h2, h3, t2, t3);
+                     lerp2(pack2(az.z, az.w), pack2(bz.z, bz.w), s, oms), lerp2(half2x2(g0.y), half2x2(g1.w), s, oms),
+                     lerp2(half2x2(g0.w), half2x2(g2.y), s, oms), lerp2(half2x2(g1.y), half2x2(g2.w), s, oms), p, t_min, t_max, h2, h3, t2, t3);
     }
     else {
         // the index is widened before it is scaled so that the address is ONE IMAD.WIDE (cur * 96 + base)
         const float4 *q = wnodes + (size_t)(unsigned)cur * (unsigned)RRTB_NODE_F4;
         float4 cx, cy, cz, hw, zr, rs;
         ldg256(q, cx, cy);     // c.x[4] c.y[4]
-        ldg256(q + 2, cz, hw); // c.z[4], bf16 pairs h.x(0,1) h.x(2,3) h.y(0,1) h.y(2,3)
-        ldg256(q + 4, zr, rs); // bf16 pairs h.z(0,1) h.z(2,3), ref[0..1] | ref[2..3], unused
+        ldg256(q + 2, cz, hw); // c.z[4], fp16 pairs h.x(0,1) h.x(2,3) h.y(0,1) h.y(2,3)
+        ldg256(q + 4, zr, rs); // fp16 pairs h.z(0,1) h.z(2,3), ref[0..1] | ref[2..3], unused
         rf = make_int4(__float_as_int(zr.z), __float_as_int(zr.w), __float_as_int(rs.x), __float_as_int(rs.y));
-        box_hit_pair(pack2(cx.x, cx.y), pack2(cy.x, cy.y), pack2(cz.x, cz.y), bf16x2(hw.x), bf16x2(hw.z), bf16x2(zr.x), p, t_min, t_max,
+        box_hit_pair(pack2(cx.x, cx.y), pack2(cy.x, cy.y), pack2(cz.x, cz.y), half2x2(hw.x), half2x2(hw.z), half2x2(zr.x), p, t_min, t_max,
                      h0, h1, t0, t1);
-        box_hit_pair(pack2(cx.z, cx.w), pack2(cy.z, cy.w), pack2(cz.z, cz.w), bf16x2(hw.y), bf16x2(hw.w), bf16x2(zr.y), p, t_min, t_max,
+        box_hit_pair(pack2(cx.z, cx.w), pack2(cy.z, cy.w), pack2(cz.z, cz.w), half2x2(hw.y), half2x2(hw.w), half2x2(zr.y), p, t_min, t_max,
                      h2, h3, t2, t3);
     }
+#ifndef RRTB_KEY_LOW2
+    // the slot replaces the low BYTE of the distance (one PRMT per child; 15 mantissa bits order the children)
+    const int k0 = h0 ? (int)__byte_perm(__float_as_uint(t0), 0x03020100u, 0x3214u) : KEY_MISS;
+    const int k1 = h1 ? (int)__byte_perm(__float_as_uint(t1), 0x03020100u, 0x3215u) : KEY_MISS;
+    const int k2 = h2 ? (int)__byte_perm(__float_as_uint(t2), 0x03020100u, 0x3216u) : KEY_MISS;
+    const int k3 = h3 ? (int)__byte_perm(__float_as_uint(t3), 0x03020100u, 0x3217u) : KEY_MISS;
+#else
     const int k0 = h0 ? (__float_as_int(t0) & ~3) : KEY_MISS;
     const int k1 = h1 ? ((__float_as_int(t1) & ~3) | 1) : KEY_MISS;
     const int k2 = h2 ? ((__float_as_int(t2) & ~3) | 2) : KEY_MISS;
     const int k3 = h3 ? ((__float_as_int(t3) & ~3) | 3) : KEY_MISS;
+#endif
     // unsigned minimum: a real key (non-negative float bits) beats KEY_MISS
     const int m = (int)min(min((unsigned)k0, (unsigned)k1), min((unsigned)k2, (unsigned)k3));
+#ifdef RRTB_TRAV_LEGACY
     if (m < 0) { // no child hit
         trav_pop(cur, sp, stk);
         return;
     }
+#endif
     // SIGNED k > m: false for the nearest (equal) and for a miss (-1)
-    RRTB_CHECK(sp >= 0 && sp + 3 <= RRTB_STACK);
-    if (k0 > m) stk[sp++] = rf.x;
-    if (k1 > m) stk[sp++] = rf.y;
-    if (k2 > m) stk[sp++] = rf.z;
-    if (k3 > m) stk[sp++] = rf.w;
+    RRTB_CHECK(trav_depth(sp, stk) >= 0 && trav_depth(sp, stk) + 3 <= RRTB_STACK);
+    trav_push_if_gt(k0, m, sp, stk, rf.x);
+    trav_push_if_gt(k1, m, sp, stk, rf.y);
+    trav_push_if_gt(k2, m, sp, stk, rf.z);
+    trav_push_if_gt(k3, m, sp, stk, rf.w);
     cur = rf.w;
     if (k2 == m) cur = rf.z;
     if (k1 == m) cur = rf.y;
     if (k0 == m) cur = rf.x;
+#ifndef RRTB_TRAV_LEGACY
+    // no child hit (every key is KEY_MISS: nothing was pushed above): pop, as predicated instructions instead of a
+    // divergent branch around the pushes
+    trav_pop_if_neg(m, cur, sp, stk);
+#endif
 }
 
 template <bool COUNT, bool MTRI = true>
 __device__ __forceinline__ void leaf_step(const float4 *__restrict__ leaves, const LeafAux info, const Ray &r,
-                                          const RayPre &p, float t_min, Hit &best, int &cur, int &sp, const int *stk,
+                                          const RayPre &p, float t_min, Hit &best, int &cur, TravSp &sp, const int *stk,
                                           TravCounters &cnt)
 {
     leaf_test<COUNT, MTRI>(leaves, info, (~cur) >> 2, (~cur) & 3, r, p, t_min, best, cnt);
@@ -623,8 +716,9 @@ __device__ __forceinline__ Hit closest_bvh(const DeviceScene &s, const Ray &r, c
     best.ref = -1;
     best.obj = -1;
     int stack[RRTB_STACK];
-    int sp = 0;
-    int cur = 0;
+    TravSp sp;
+    int cur;
+    trav_begin(cur, sp, stack);
     if (s.motion) { // interpolating nodes: where the ray's time lies in the shutter
         RayPre pm = p;
         pm.s = (r.tm - s.shutter_open) * s.shutter_inv;

@@ -175,20 +175,23 @@ __device__ __forceinline__ void leaf_test_d(const float4 *__restrict__ leaves, c
         else ++cnt.tri;
     }
     const float4 *rec = leaves + (size_t)(unsigned)slot * 3u; // one IMAD.WIDE (slot * 48 + base)
-    float4 a = __ldg(rec);
     double t;
     bool h;
-    if (type == PRIM_SPHERE) {
-        h = sphere_test_d(r, (double)a.x, (double)a.y, (double)a.z, (double)a.w, t_min, best.t, t);
+    if (type == PRIM_SPHERE) { // centre and radius as doubles in the second and third float4 (k_prepare)
+        const float4 b = __ldg(rec + 1), c = __ldg(rec + 2);
+        h = sphere_test_d(r, __hiloint2double(__float_as_int(b.y), __float_as_int(b.x)),
+                          __hiloint2double(__float_as_int(b.w), __float_as_int(b.z)),
+                          __hiloint2double(__float_as_int(c.y), __float_as_int(c.x)),
+                          __hiloint2double(__float_as_int(c.w), __float_as_int(c.z)), t_min, best.t, t);
     }
     else if (type == PRIM_MSPHERE) {
-        float4 b = __ldg(rec + 1), c = __ldg(rec + 2);
+        float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
         double cx, cy, cz;
         msphere_center_d(a, b, c, r.tm, cx, cy, cz);
         h = sphere_test_d(r, cx, cy, cz, (double)a.w, t_min, best.t, t);
     }
     else {
-        float4 b = __ldg(rec + 1), c = __ldg(rec + 2);
+        float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
         double v0x = a.x, v0y = a.y, v0z = a.z;
         if (type == PRIM_MTRIANGLE) {
             v0x = __fma_rn((double)a.w, r.tm, v0x);
@@ -233,8 +236,9 @@ __device__ __forceinline__ HitD closest_bvh_d(const DeviceScene &s, const RayD &
     const RayPre p = ray_pre_d(r);
     const float t_min_f = __double2float_rd(t_min);
     int stack[RRTB_STACK];
-    int sp = 0;
-    int cur = 0;
+    TravSp sp;
+    int cur;
+    trav_begin(cur, sp, stack);
     RayPre pm = p;
     if (s.motion) pm.s = (__double2float_rn(r.tm) - s.shutter_open) * s.shutter_inv;
     while (cur != TRAV_DONE) {

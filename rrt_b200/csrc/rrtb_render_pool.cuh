@@ -74,7 +74,7 @@ struct PathF32 { // the float integrator (rrtb_device.cuh)
     }
     template <bool COUNT, bool MTRI>
     static __device__ __forceinline__ void leaf(const float4 *__restrict__ leaves, const LeafAux info, const Ray &r,
-                                                const RayPre &p, Hit &best, int &cur, int &sp, const int *stk, TravCounters &tc)
+                                                const RayPre &p, Hit &best, int &cur, TravSp &sp, const int *stk, TravCounters &tc)
     {
         leaf_step<COUNT, MTRI>(leaves, info, r, p, 0.001f, best, cur, sp, stk, tc);
     }
@@ -128,7 +128,7 @@ struct PathF64 { // the double integrator (rrtb_device_f64.cuh); bit-exact again
     }
     template <bool COUNT, bool MTRI>
     static __device__ __forceinline__ void leaf(const float4 *__restrict__ leaves, const LeafAux info, const RayD &r,
-                                                const RayPre &, HitD &best, int &cur, int &sp, const int *stk, TravCounters &tc)
+                                                const RayPre &, HitD &best, int &cur, TravSp &sp, const int *stk, TravCounters &tc)
     {
         leaf_test_d<COUNT>(leaves, info, (~cur) >> 2, (~cur) & 3, r, 0.001, best, tc);
         trav_pop(cur, sp, stk);
@@ -188,8 +188,9 @@ __global__ void __launch_bounds__(RENDER_TPB, P::BLOCKS_PER_SM) k_render_pool(co
     int slot = -1;
     typename P::RayT ray;
     RayPre pre;
-    int cur = TRAV_DONE, sp = 0;
+    int cur = TRAV_DONE;
     int stack[RRTB_STACK];
+    TravSp sp = TravSp();
     typename P::HitT best = P::make_hit((real)0, -1);
     bool queue_empty = false; // the global work queue has run dry (warp-uniform)
     unsigned long long rays = 0, hits = 0;
@@ -215,8 +216,7 @@ __global__ void __launch_bounds__(RENDER_TPB, P::BLOCKS_PER_SM) k_render_pool(co
                 if (MOTION) pre.s = ((float)ray.tm - s.shutter_open) * s.shutter_inv; // where the ray's time lies in the shutter
                 best.t = P::inf();
                 best.ref = -1;
-                cur = 0;
-                sp = 0;
+                trav_begin(cur, sp, stack);
             }
             tq_n -= take;
         }

@@ -26,7 +26,7 @@ class LabCounters(C.Structure):
 def lab():
     so = os.path.join(ROOT, "tools", "treelab", "libtreelab.so")
     lib = C.CDLL(so)
-    for f in ("lab_build_sah", "lab_from_arrays", "lab_collapse", "lab_build_ploc", "lab_build_hybrid"):
+    for f in ("lab_build_sah", "lab_from_arrays", "lab_collapse", "lab_build_ploc", "lab_build_hybrid", "lab_build_hybrid2"):
         getattr(lib, f).restype = C.c_void_p
     lib.lab_sah_cost.restype = C.c_double
     lib.lab_sah_cost.argtypes = [C.c_void_p]
@@ -92,6 +92,11 @@ def run(scene, rays, label=""):
     for bins in (8, 16, 32):
         L.lab_set_sah(0, bins)
         trees["hyb512b%d" % bins] = C.c_void_p(L.lab_build_hybrid(trees["lbvh"], 512))
+    # a second SAH level over the roots of those subtrees (<= 512 / 4096 roots per upper subtree), and larger subtrees
+    L.lab_set_sah(0, 32)
+    trees["hyb2_512_512"] = C.c_void_p(L.lab_build_hybrid2(trees["lbvh"], 512, 512))
+    trees["hyb2_512_4096"] = C.c_void_p(L.lab_build_hybrid2(trees["lbvh"], 512, 4096))
+    trees["hyb2048b32"] = C.c_void_p(L.lab_build_hybrid(trees["lbvh"], 2048))
     L.lab_set_sah(4096, 32)
     trees["hyb512sweep"] = C.c_void_p(L.lab_build_hybrid(trees["lbvh"], 512))
     for r in ():

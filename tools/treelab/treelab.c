@@ -83,6 +83,28 @@ static int hybrid_rec(const btree *src,btree *dst,int c,int max_leaves,int *next
   if(nl<=max_leaves){ int *ids=malloc(sizeof(int)*nl); int k=0; collect(src,c,ids,&k); int r=sah_rec(dst,ids,nl,next); free(ids); return r; }
   int node=(*next)++; int l=hybrid_rec(src,dst,src->left[c],max_leaves,next); int r=hybrid_rec(src,dst,src->right[c],max_leaves,next); dst->left[node]=l; dst->right[node]=r; return node; }
 btree *lab_build_hybrid(const btree *src,int max_leaves){ btree *t=lab_tree_new(src->n,(const float*)src->pbox); int next=0; t->root=hybrid_rec(src,t,src->root,max_leaves,&next); refit(t,t->root); return t; }
+/* two levels: the subtrees of <= max_leaves leaves as above, then every maximal upper subtree with <= max_items of those
+ * subtree roots (or single leaves) below it is rebuilt by the SAH builder over the ROOTS' boxes (one more thread block per
+ * upper subtree on the GPU); only the few nodes above those keep the Morton topology */
+static int count_items(const btree *t,int c,int max_leaves){ if(c<0) return 1; if(count_leaves(t,c)<=max_leaves) return 1; return count_items(t,t->left[c],max_leaves)+count_items(t,t->right[c],max_leaves); }
+static void collect_items(const btree *src,btree *dst,int c,int max_leaves,int *next,int *refs,int *n){
+  if(c<0){refs[(*n)++]=c;return;}
+  int nl=count_leaves(src,c);
+  if(nl<=max_leaves){ int *ids=malloc(sizeof(int)*nl); int k=0; collect(src,c,ids,&k); refs[(*n)++]=sah_rec(dst,ids,nl,next); free(ids); return; }
+  collect_items(src,dst,src->left[c],max_leaves,next,refs,n); collect_items(src,dst,src->right[c],max_leaves,next,refs,n); }
+static int graft(const btree *tmp,btree *dst,int c,const int *refs,int *next){ if(c<0) return refs[~c]; int node=(*next)++; int l=graft(tmp,dst,tmp->left[c],refs,next); int r=graft(tmp,dst,tmp->right[c],refs,next); dst->left[node]=l; dst->right[node]=r; return node; }
+static int hybrid2_rec(const btree *src,btree *dst,int c,int max_leaves,int max_items,int *next){
+  if(c<0) return c;
+  int nl=count_leaves(src,c);
+  if(nl<=max_leaves){ int *ids=malloc(sizeof(int)*nl); int k=0; collect(src,c,ids,&k); int r=sah_rec(dst,ids,nl,next); free(ids); return r; }
+  int ni=count_items(src,c,max_leaves);
+  if(ni<=max_items){
+    int *refs=malloc(sizeof(int)*ni); int k=0; collect_items(src,dst,c,max_leaves,next,refs,&k);
+    box_t *ib=malloc(sizeof(box_t)*ni); for(int i=0;i<ni;i++) ib[i]=refit(dst,refs[i]);
+    btree *tmp=lab_tree_new(ni,(const float*)ib); int *ids=malloc(sizeof(int)*ni); for(int i=0;i<ni;i++)ids[i]=i; int tn=0; int troot=sah_rec(tmp,ids,ni,&tn);
+    int r=graft(tmp,dst,troot,refs,next); free(ids); free(ib); free(refs); return r; }
+  int node=(*next)++; int l=hybrid2_rec(src,dst,src->left[c],max_leaves,max_items,next); int r=hybrid2_rec(src,dst,src->right[c],max_leaves,max_items,next); dst->left[node]=l; dst->right[node]=r; return node; }
+btree *lab_build_hybrid2(const btree *src,int max_leaves,int max_items){ btree *t=lab_tree_new(src->n,(const float*)src->pbox); int next=0; t->root=hybrid2_rec(src,t,src->root,max_leaves,max_items,&next); refit(t,t->root); return t; }
 double lab_sah_cost(const btree *t){ double ra=box_area(&t->box[t->root]),c=0; for(int i=0;i<t->n-1;i++){ c+=box_area(&t->box[i])/ra*2.0; } return c; }
 
 /* ---- ray/box ---- */
