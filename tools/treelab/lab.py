@@ -26,12 +26,13 @@ class LabCounters(C.Structure):
 def lab():
     so = os.path.join(ROOT, "tools", "treelab", "libtreelab.so")
     lib = C.CDLL(so)
-    for f in ("lab_build_sah", "lab_from_arrays", "lab_collapse", "lab_build_ploc", "lab_build_hybrid", "lab_build_hybrid2"):
+    for f in ("lab_build_sah", "lab_from_arrays", "lab_collapse", "lab_build_ploc", "lab_build_hybrid", "lab_build_hybrid2", "lab_collapse_dp"):
         getattr(lib, f).restype = C.c_void_p
     lib.lab_sah_cost.restype = C.c_double
     lib.lab_sah_cost.argtypes = [C.c_void_p]
     lib.lab_wide_fill.restype = C.c_double
     lib.lab_wide_fill.argtypes = [C.c_void_p]
+    lib.lab_set_cleaf.argtypes = [C.c_double]
     return lib
 
 
@@ -109,7 +110,12 @@ def run(scene, rays, label=""):
         print("%-22s sahcost %7.2f  " % (label + name + " bin", L.lab_sah_cost(t)), c.d())
         for k in (4,):
             for q in (0,):
-                w = C.c_void_p(L.lab_collapse(t, k))
+              for mode in ("greedy", "dp1.0"):
+                if mode == "greedy":
+                    w = C.c_void_p(L.lab_collapse(t, k))
+                else:
+                    L.lab_set_cleaf(float(mode[2:]))
+                    w = C.c_void_p(L.lab_collapse_dp(t, k))
                 L.lab_quantise(w, q)
                 L.lab_axis_sort(w)
                 for cull, om in ((0, 1),):
@@ -117,7 +123,7 @@ def run(scene, rays, label=""):
                     c = LabCounters()
                     L.lab_trace_wide(w, C.byref(o._s), vp(rays), m, C.c_float(0.001), cull, C.byref(c), vp(ids))
                     assert np.array_equal(ids, ref_ids), (name, k)
-                    print("%-22s nodes %7d fill %.2f " % ("%s%s w%d q%d cull%d om%d" % (label, name, k, q, cull, om), L.lab_wide_nodes(w),
+                    print("%-30s nodes %7d fill %.2f " % ("%s%s w%d %s" % (label, name, k, mode), L.lab_wide_nodes(w),
                                                           L.lab_wide_fill(w)), c.d())
 
 

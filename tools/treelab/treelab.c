@@ -139,6 +139,30 @@ static int collapse_rec(const btree *t,wtree *w,int bnode){
   for(int i=0;i<nc;i++){ w->child[me*k+i]= ch[i]>=0? collapse_rec(t,w,ch[i]) : ch[i]; }
   return me;
 }
+/* SAH-optimal collapse (after Ylitie et al. 2017): F[v][j] = least cost of covering subtree(v) with at most j wide-node
+ * children; a child that is an internal binary node becomes a wide node of cost area + the best cover of its two sides
+ * with k children in total, a leaf child costs c_leaf * area */
+static double g_cleaf=1.0; void lab_set_cleaf(double c){g_cleaf=c;}
+typedef struct { double F[9]; int split[9]; double own; int own_split; } dpent;
+static void dp_rec(const btree *t,int v,int k,dpent *D){ /* v >= 0 */
+  int l=t->left[v], r=t->right[v]; if(l>=0)dp_rec(t,l,k,D); if(r>=0)dp_rec(t,r,k,D);
+  double Fl[9],Fr[9]; for(int j=1;j<=k;j++){ Fl[j]= l>=0? D[l].F[j] : g_cleaf*box_area(&t->pbox[~l]); Fr[j]= r>=0? D[r].F[j] : g_cleaf*box_area(&t->pbox[~r]); }
+  double best=INFINITY; int bs=1; for(int i=1;i<k;i++){ double c=Fl[i]+Fr[k-i]; if(c<best){best=c;bs=i;} }
+  D[v].own=box_area(&t->box[v])+best; D[v].own_split=bs;
+  D[v].F[1]=D[v].own; D[v].split[1]=0;
+  for(int j=2;j<=k;j++){ double b=D[v].F[j-1]; int sp=D[v].split[j-1]; /* at most j: not worse than at most j-1 */
+    for(int i=1;i<j;i++){ double c=Fl[i]+Fr[j-i]; if(c<b){b=c;sp=i+100*j;} } D[v].F[j]=b; D[v].split[j]=sp; } }
+static void dp_cut(const btree *t,const dpent *D,int v,int j,int *out,int *n){ /* children covering subtree(v) with at most j roots */
+  if(v<0){out[(*n)++]=v;return;}
+  int sp=D[v].split[j]; if(sp==0){out[(*n)++]=v;return;} int jj=sp/100,i=sp%100; dp_cut(t,D,t->left[v],i,out,n); dp_cut(t,D,t->right[v],jj-i,out,n); }
+static int collapse_dp_rec(const btree *t,const dpent *D,wtree *w,int bnode){
+  int me=w->n_nodes++; int k=w->k; int ch[16]; int nc=0; int i=D[bnode].own_split;
+  dp_cut(t,D,t->left[bnode],i,ch,&nc); dp_cut(t,D,t->right[bnode],k-i,ch,&nc);
+  for(int q=0;q<k;q++){ if(q<nc){ w->cbox[me*k+q]= ch[q]>=0? t->box[ch[q]] : t->pbox[~ch[q]]; } else w->child[me*k+q]=W_EMPTY; }
+  for(int q=0;q<nc;q++){ w->child[me*k+q]= ch[q]>=0? collapse_dp_rec(t,D,w,ch[q]) : ch[q]; }
+  return me; }
+wtree *lab_collapse_dp(const btree *t,int k){ wtree *w=calloc(1,sizeof(wtree)); w->k=k; w->child=malloc(sizeof(int)*t->n*k); w->cbox=malloc(sizeof(box_t)*t->n*k); w->n_nodes=0; w->axis=NULL;
+  if(t->n>1){ dpent *D=calloc(t->n,sizeof(dpent)); dp_rec(t,t->root,k,D); collapse_dp_rec(t,D,w,t->root); free(D);} return w; }
 wtree *lab_collapse(const btree *t,int k){ wtree *w=calloc(1,sizeof(wtree)); w->k=k; w->child=malloc(sizeof(int)*t->n*k); w->cbox=malloc(sizeof(box_t)*t->n*k); w->n_nodes=0; if(t->n>1)collapse_rec(t,w,t->root); w->axis=NULL; return w; }
 /* sort each node's children ascending along the axis with the largest spread of child-box centres (empties last) */
 void lab_axis_sort(wtree *w){ int k=w->k; w->axis=malloc(sizeof(int)*w->n_nodes);
