@@ -553,36 +553,7 @@ __device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b)
 // The stack grows upwards from stk[1]; stk[0] holds TRAV_DONE, so the pop that empties the stack ends the traversal
 // without a test.  TravSp points at the next free entry (a local-memory address kept in a register instead of an index
 // that every access scales and adds to the frame: 218 -> 196 SASS instructions per two visits together with the
-// branch-free visit and the PRMT keys).  -DRRTB_TRAV_LEGACY / -DRRTB_KEY_LOW2 build the round-1 forms for A/B runs.
-#ifndef RRTB_TRAV_LEGACY
-#ifdef RRTB_TRAV_ASM
-// the same with the stack pointer as a 32-bit .local address and every access in PTX, so that a conditional push is
-// exactly a predicated STL and a predicated add (nvcc's if-conversion of `if (c) *sp++ = ref` costs a third instruction)
-typedef unsigned TravSp;
-__device__ __forceinline__ void trav_pop(int &cur, TravSp &sp, const int *)
-{
-    asm volatile("ld.local.b32 %0, [%1+-4];\n\tadd.u32 %1, %1, -4;" : "=r"(cur), "+r"(sp));
-}
-__device__ __forceinline__ void trav_pop_if_neg(int m, int &cur, TravSp &sp, const int *) // if (m < 0) pop
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, 0;\n\t@p ld.local.b32 %0, [%1+-4];\n\t@p add.u32 %1, %1, -4;\n\t}"
-                 : "+r"(cur), "+r"(sp)
-                 : "r"(m));
-}
-__device__ __forceinline__ void trav_push_if_gt(int k, int m, TravSp &sp, int *, int ref) // if (k > m) push ref
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %2, %3;\n\t@p st.local.b32 [%0], %1;\n\t@p add.u32 %0, %0, 4;\n\t}"
-                 : "+r"(sp)
-                 : "r"(ref), "r"(k), "r"(m));
-}
-__device__ __forceinline__ void trav_begin(int &cur, TravSp &sp, int *stk)
-{
-    cur = 0;
-    sp = (unsigned)__cvta_generic_to_local(stk);
-    asm volatile("st.local.b32 [%0], %1;\n\tadd.u32 %0, %0, 4;" : "+r"(sp) : "r"(TRAV_DONE));
-}
-__device__ __forceinline__ int trav_depth(TravSp sp, const int *stk) { return (int)(sp - (unsigned)__cvta_generic_to_local(stk)) >> 2; }
-#else
+// branch-free visit and the PRMT keys; measured with the round-1 forms as variant builds, profiles/README.md).
 typedef int *TravSp;
 __device__ __forceinline__ void trav_pop(int &cur, TravSp &sp, const int *) { cur = *--sp; }
 __device__ __forceinline__ void trav_pop_if_neg(int m, int &cur, TravSp &sp, const int *)
@@ -593,6 +564,7 @@ __device__ __forceinline__ void trav_push_if_gt(int k, int m, TravSp &sp, int *,
 {
     if (k > m) *sp++ = ref;
 }
+// start a traversal at the root
 __device__ __forceinline__ void trav_begin(int &cur, TravSp &sp, int *stk)
 {
     cur = 0;
@@ -600,21 +572,6 @@ __device__ __forceinline__ void trav_begin(int &cur, TravSp &sp, int *stk)
     sp = stk + 1;
 }
 __device__ __forceinline__ int trav_depth(TravSp sp, const int *stk) { return (int)(sp - stk); }
-#endif
-#else
-typedef int TravSp;
-__device__ __forceinline__ void trav_pop(int &cur, TravSp &sp, const int *stk) { cur = sp > 0 ? stk[--sp] : TRAV_DONE; }
-__device__ __forceinline__ void trav_push_if_gt(int k, int m, TravSp &sp, int *stk, int ref)
-{
-    if (k > m) stk[sp++] = ref;
-}
-__device__ __forceinline__ void trav_begin(int &cur, TravSp &sp, int *)
-{
-    cur = 0;
-    sp = 0;
-}
-__device__ __forceinline__ int trav_depth(TravSp sp, const int *) { return sp; }
-#endif
 
 // t_min must be >= 0 (keys order as integers only for non-negative distances); rrtb_trace_closest checks it
 // (1 - s) a + s b on an FP32x2 pair
@@ -661,26 +618,13 @@ __device__ __forceinline__ void wide_step(const float4 *__restrict__ wnodes, con
         box_hit_pair(pack2(cx.z, cx.w), pack2(cy.z, cy.w), pack2(cz.z, cz.w), half2x2(hw.y), half2x2(hw.w), half2x2(zr.y), p, t_min, t_max,
                      h2, h3, t2, t3);
     }
-#ifndef RRTB_KEY_LOW2
     // the slot replaces the low BYTE of the distance (one PRMT per child; 15 mantissa bits order the children)
     const int k0 = h0 ? (int)__byte_perm(__float_as_uint(t0), 0x03020100u, 0x3214u) : KEY_MISS;
     const int k1 = h1 ? (int)__byte_perm(__float_as_uint(t1), 0x03020100u, 0x3215u) : KEY_MISS;
     const int k2 = h2 ? (int)__byte_perm(__float_as_uint(t2), 0x03020100u, 0x3216u) : KEY_MISS;
     const int k3 = h3 ? (int)__byte_perm(__float_as_uint(t3), 0x03020100u, 0x3217u) : KEY_MISS;
-#else
-    const int k0 = h0 ? (__float_as_int(t0) & ~3) : KEY_MISS;
-    const int k1 = h1 ? ((__float_as_int(t1) & ~3) | 1) : KEY_MISS;
-    const int k2 = h2 ? ((__float_as_int(t2) & ~3) | 2) : KEY_MISS;
-    const int k3 = h3 ? ((__float_as_int(t3) & ~3) | 3) : KEY_MISS;
-#endif
     // unsigned minimum: a real key (non-negative float bits) beats KEY_MISS
     const int m = (int)min(min((unsigned)k0, (unsigned)k1), min((unsigned)k2, (unsigned)k3));
-#ifdef RRTB_TRAV_LEGACY
-    if (m < 0) { // no child hit
-        trav_pop(cur, sp, stk);
-        return;
-    }
-#endif
     // SIGNED k > m: false for the nearest (equal) and for a miss (-1)
     RRTB_CHECK(trav_depth(sp, stk) >= 0 && trav_depth(sp, stk) + 3 <= RRTB_STACK);
     trav_push_if_gt(k0, m, sp, stk, rf.x);
@@ -691,11 +635,9 @@ __device__ __forceinline__ void wide_step(const float4 *__restrict__ wnodes, con
     if (k2 == m) cur = rf.z;
     if (k1 == m) cur = rf.y;
     if (k0 == m) cur = rf.x;
-#ifndef RRTB_TRAV_LEGACY
     // no child hit (every key is KEY_MISS: nothing was pushed above): pop, as predicated instructions instead of a
     // divergent branch around the pushes
     trav_pop_if_neg(m, cur, sp, stk);
-#endif
 }
 
 template <bool COUNT, bool MTRI = true>
