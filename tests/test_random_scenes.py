@@ -91,3 +91,79 @@ def test_gpu_vs_oracle_on_random_scenes(ctx, seed):
     ref, _, cnt = orc.render(64, 40, 4, 50, seed)
     assert st["paths"] == cnt["paths"] and abs(st["rays"] - cnt["rays"]) <= 0.02 * cnt["rays"] + 8
     assert np.mean(np.abs(np.sqrt(img / 4) - np.sqrt(ref / 4)).max(axis=2) < 2e-3) > 0.95
+
+
+def special_rays(seed, scene):
+    """The rays that break slab tests and discriminants: directions with one or two components exactly zero, rays that
+    graze a sphere (aimed at a point of its silhouette), rays inside a triangle's plane, very long and very short
+    direction vectors."""
+    rng = np.random.default_rng(seed + 7000)
+    out = []
+    # axis-parallel and plane-parallel directions through the cloud of objects
+    for zero in ((1, 2), (0, 2), (0, 1), (0,), (1,), (2,)):
+        r = np.zeros((500, 7), np.float32)
+        r[:, 0:3] = rng.uniform(-9, 9, size=(500, 3))
+        d = rng.uniform(-2, 2, size=(500, 3))
+        d[:, list(zero)] = 0.0
+        r[:, 3:6] = d
+        out.append(r)
+    # grazing rays: from a random origin towards a point at distance (1 +- 1e-6) radius from a sphere's centre, in the
+    # plane perpendicular to the line of sight
+    c = scene.spheres["center"][1:].astype(np.float64)
+    rad = scene.spheres["radius"][1:].astype(np.float64)
+    k = rng.integers(0, len(c), size=3000)
+    o = rng.uniform(-9, 9, size=(3000, 3))
+    los = c[k] - o
+    los /= np.linalg.norm(los, axis=1, keepdims=True)
+    side = np.cross(los, rng.normal(size=(3000, 3)))
+    side /= np.linalg.norm(side, axis=1, keepdims=True)
+    eps = rng.choice([-1e-3, -1e-5, -1e-6, 0.0, 1e-6, 1e-5, 1e-3], size=(3000, 1))
+    r = np.zeros((3000, 7), np.float32)
+    r[:, 0:3] = o
+    r[:, 3:6] = c[k] + side * rad[k, None] * (1.0 + eps) - o
+    out.append(r)
+    # rays inside the plane of a triangle (from outside it, through its centroid) and through its vertices / edges
+    t = scene.triangles
+    k = rng.integers(0, len(t), size=2000)
+    v0, v1, v2 = (t[n][k].astype(np.float64) for n in ("v0", "v1", "v2"))
+    w = rng.dirichlet((1, 1, 1), size=2000)
+    w[:700] = np.eye(3)[rng.integers(0, 3, size=700)]  # exactly a vertex
+    w[700:1400, 0] = 0.0
+    w[700:1400] /= np.maximum(w[700:1400].sum(axis=1, keepdims=True), 1e-9)  # on the edge v1 v2
+    p = w[:, 0:1] * v0 + w[:, 1:2] * v1 + w[:, 2:3] * v2
+    o = rng.uniform(-9, 9, size=(2000, 3))
+    o[1400:1700] = (v0 + 3.0 * (v1 - v0))[1400:1700]  # origin in the triangle's plane
+    r = np.zeros((2000, 7), np.float32)
+    r[:, 0:3] = o
+    r[:, 3:6] = p - o
+    out.append(r)
+    # direction lengths from 1e-6 to 1e6
+    r = np.zeros((1500, 7), np.float32)
+    r[:, 0:3] = rng.uniform(-9, 9, size=(1500, 3))
+    d = rng.uniform(-5, 5, size=(1500, 3)) - r[:, 0:3]
+    r[:, 3:6] = d * np.exp(rng.uniform(np.log(1e-6), np.log(1e6), size=(1500, 1)))
+    out.append(r)
+    rays = np.concatenate(out).astype(np.float32)
+    rays[:, 6] = rng.uniform(scene.camera["time0"][0], max(scene.camera["time1"][0], 1e-3), size=len(rays))
+    ok = np.abs(rays[:, 3:6]).max(axis=1) > 0  # a zero direction is not a ray
+    return rays[ok]
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(3))
+def test_oracle_vs_reference_double_on_special_rays(seed):
+    """Knife-edge rays (grazing, in-plane, through vertices) may fall either side of a surface in float and in double: the
+    bar is 99.5 % equal ids there, and the oracle's own two paths (flat scan, LBVH traversal with its conservative slab
+    test) must agree EXACTLY on every ray -- zero direction components included."""
+    scene = random_scene(40 + seed)
+    rays = special_rays(seed, scene)
+    ref_id, ref_t = RefWorld(scene, "d").trace_scan(rays)
+    orc = Oracle(scene)
+    ids_s, t_s = orc.trace(rays, 0.001, "scan")
+    ids_b, t_b = orc.trace(rays, 0.001, "bvh")
+    assert np.array_equal(ids_s, ids_b) and t_s.tobytes() == t_b.tobytes()
+    same = ids_s == ref_id
+    m = same & (ref_id >= 0)
+    rel = np.abs(t_s[m].astype(np.float64) - ref_t[m]) / np.abs(ref_t[m])
+    assert same.mean() >= 0.995, (seed, same.mean(), int((~same).sum()))
+    assert np.mean(rel <= 1e-5) >= 0.999, (seed, rel.max())
