@@ -107,3 +107,31 @@ def test_cli_multi_gpu_is_bit_identical(tmp_path, built_lib):
         assert r.returncode == 0, r.stderr
         outs.append(np.asarray(Image.open(out)))
     assert np.array_equal(outs[0], outs[1])
+
+
+REF_ANIM = "/root/reference/scenes/final_anim/anim.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ANIM), reason="needs the reference's scenes/final_anim/anim.py (this container only)")
+def test_camera_path_equals_the_reference_generator(tmp_path, built_lib):
+    """the reference's animation is 261 scene files written by scenes/final_anim/anim.py, which differ only in
+    their camera line.  The generator is EXECUTED here (in a scratch directory), every file goes through the product's
+    parser, and the derived camera must equal rrt_b200.anim.final_anim_cameras bit for bit; materials and spheres must be
+    those of frame 0 in every frame (which is what lets a batch upload the scene once)."""
+    from rrt_b200 import Scene
+    from rrt_b200.anim import final_anim_cameras
+
+    r = subprocess.run(["python3", REF_ANIM], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    files = sorted(p for p in os.listdir(tmp_path) if p.startswith("z_") and p.endswith(".txt"))
+    assert len(files) == 261
+    W, H = 1280, 720  # scenes/final_anim/Makefile:9-10
+    cams = final_anim_cameras(W, H, n_frames=261)
+    first = None
+    for i in range(261):
+        a = Scene.from_file(tmp_path / files[i], W, H).arrays
+        assert a.camera.tobytes() == cams[i].tobytes(), i
+        if first is None:
+            first = a
+        assert a.materials.tobytes() == first.materials.tobytes() and a.spheres.tobytes() == first.spheres.tobytes()
+    assert len(first.spheres) == 488
