@@ -229,3 +229,17 @@ def test_parser_fuzz_vs_live_reference_parser(seed, tmp_path, built_lib):
         assert getattr(got.arrays, k).tobytes() == getattr(want, k).tobytes(), (seed, k)
     c = got.counts()
     assert [c[k] for k in ("materials", "spheres", "mspheres", "triangles", "objs", "obj_insts")] == [ref.counts[k] for k in ("materials", "spheres", "mspheres", "triangles", "objs", "obj_insts")]
+
+
+def test_parser_survives_mutated_scenes_under_sanitizers():
+    """tools/fuzz_parser.sh: rrtb_host.cpp built with AddressSanitizer + UBSan parses 300 mutated copies of the reference's
+    scenes (truncated, shuffled, keyword / nan / inf / huge-number substitutions, random bytes): it may reject them, it
+    may not crash, read out of bounds or leak."""
+    import shutil
+
+    scenes = "/root/reference/scenes" if os.path.isdir("/root/reference/scenes") else os.path.join(ROOT, "oracle", "_ref", "scenes")
+    if not os.path.isdir(scenes) or shutil.which("g++") is None:
+        pytest.skip("needs the reference's scene files and g++")
+    r = subprocess.run(["bash", os.path.join(ROOT, "tools", "fuzz_parser.sh"), "300", scenes], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sanitizer findings 0" in r.stdout
