@@ -64,6 +64,8 @@ class Counters(C.Structure):
 
 
 def build_oracle():
+    if os.environ.get("RRTB_ORACLE_LIB"):  # e.g. oracle/liboracle_ubsan.so (`make -C oracle ubsan`): the checker under UBSan
+        return os.environ["RRTB_ORACLE_LIB"]
     so = os.path.join(ORACLE_DIR, "liboracle.so")
     src = [os.path.join(ORACLE_DIR, f) for f in ("rrt_oracle.c", "rrt_oracle_f64.c", "rrt_oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
